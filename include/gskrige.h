@@ -1,0 +1,173 @@
+/*
+ * gskrige.h — C ABI of libgskrige.so: B200-native Kriging estimation.
+ *
+ * This is the drop-in boundary for ONE hot path of juliohm/GeoStatsSolvers.jl:
+ * the two internal functions
+ *
+ *     exactsolve(problem, var, preproc)   -> (varμ, varσ)   ref: src/estimation/krig.jl:166-186
+ *     approxsolve(problem, var, preproc)  -> (varμ, varσ)   ref: src/estimation/krig.jl:188-234
+ *
+ * called from solve(problem, ::KrigingSolver) at ref: src/estimation/krig.jl:151-157.
+ * Everything above these two calls (problem construction, units, missing-value
+ * filtering, per-variable loop, georef of the result) stays host code (Julia shim in
+ * julia/GSKrige.jl, Python mirror in geostatssolvers.jl_b200/). Everything below —
+ * neighbour search, variogram evaluation, kriging-system assembly, factorisation,
+ * weight solve, mean/variance — runs in hand-written sm_100a CUDA kernels.
+ *
+ * The reference has no FFI of its own; the entry points below are what a `ccall`
+ * from the Julia shim binds. Plain pointers and sizes only,
+ * no C++/torch types. All arrays are caller-owned; the library never keeps a host
+ * pointer after a call returns. There is NO CPU fallback: every compute entry point
+ * fails with GSK_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef GSKRIGE_H
+#define GSKRIGE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSK_ABI_VERSION 1
+
+/* ---- enumerations (values are ABI) ------------------------------------------------ */
+
+/* variogram family — ref call site: test/estimation/krig.jl:10 (GaussianVariogram(range=35.0, nugget=0.0));
+ * formulas are Variography 0.22's (ref: Project.toml:42), restated in oracle/gsk_oracle.c */
+enum { GSK_VARIO_GAUSSIAN = 0, GSK_VARIO_SPHERICAL = 1, GSK_VARIO_EXPONENTIAL = 2 };
+
+/* estimator — selection precedence is host logic, ref: src/ui.jl:40-50 (kriging_ui) */
+enum { GSK_EST_SIMPLE = 0, GSK_EST_ORDINARY = 1, GSK_EST_UNIVERSAL = 2 };
+
+/* flags */
+enum {
+  GSK_FLAG_CLAMP_VARIANCE = 1u << 0, /* σ² = max(0, σ²)  (GeoStatsModels predictvar)            */
+  GSK_FLAG_SQRT_ROUNDTRIP = 1u << 1, /* σ² -> (sqrt σ²)²  (Normal(μ,√σ²) then var(), krig.jl:183,231) */
+  GSK_FLAGS_DEFAULT = (1u << 0) | (1u << 1)
+};
+
+/* return codes */
+enum {
+  GSK_OK = 0,
+  GSK_ERR_INVALID = -1,     /* bad argument (message says which)                              */
+  GSK_ERR_UNSUPPORTED = -2, /* option outside the hot path (drifts, non-Euclidean metric, …)  */
+  GSK_ERR_CUDA = -3,        /* CUDA runtime failure / no sm_100 device                        */
+  GSK_ERR_NOMEM = -4,       /* host or device allocation failed                               */
+  GSK_ERR_STATE = -5        /* call order violation (execute before plan, …)                  */
+};
+
+/* limits of the local (maxneighbors) kernels */
+#define GSK_MAX_NEIGHBORS 96
+#define GSK_MAX_SUPPORT 125 /* block-support sub-sample points per target cell */
+#define GSK_MAX_DRIFT_TERMS 10 /* C(3+2,2): universal kriging up to degree 2 in 3-D */
+
+/* ---- the problem description ------------------------------------------------------ */
+
+typedef struct gsk_problem {
+  int32_t abi_version; /* = GSK_ABI_VERSION */
+  int32_t dim;         /* 1, 2 or 3 (embeddim of sample and target domains) */
+
+  /* samples: the NON-MISSING subset the host built at krig.jl:97-107, SoA, units stripped
+   * (utils.jl:10-15). Neighbour indices reported back refer to this subset (0-based). */
+  int64_t n_samples;
+  const double *coords[3]; /* each length n_samples; unused dims may be NULL */
+  const double *values;    /* length n_samples */
+
+  /* targets: a CartesianGrid (column-major / x-fastest linear index, pinned by
+   * ref test/estimation/krig.jl:34-37,69-72) when grid_dims[0] > 0 … */
+  int64_t grid_dims[3]; /* unused dims = 1 */
+  double grid_origin[3];
+  double grid_spacing[3];
+  /* … or an explicit point list (PointSet domains, ref: src/simulation/fft.jl:113-114) when grid_dims[0] == 0 */
+  int64_t n_points;
+  const double *point_coords[3];
+
+  /* slab of the linear target range this call computes (multi-GPU sharding).
+   * target_count < 0 means "through the end". Output arrays are slab-local. */
+  int64_t target_first;
+  int64_t target_count;
+
+  /* block support of a target (Variography's geometry sub-sampling):
+   * n_support offsets relative to the target centroid; n_support = 1 with a zero offset
+   * is point support. */
+  int32_t n_support;
+  const double *support_offsets[3]; /* each length n_support; unused dims may be NULL */
+
+  /* variogram */
+  int32_t vario_kind;
+  double vario_range, vario_sill, vario_nugget;
+  double gaussian_nugget_eps; /* Variography adds 1e-6 to a Gaussian nugget; 0 switches it off */
+
+  /* estimator */
+  int32_t estimator;
+  double sk_mean;    /* Simple Kriging mean */
+  int32_t uk_degree; /* Universal Kriging polynomial degree (0..2) */
+
+  /* neighbourhood — ref: src/ui.jl:11-32 (searcher_ui), krig.jl:113-117,213 */
+  int32_t min_neighbors; /* targets with fewer neighbours -> NaN (the host maps to `missing`) */
+  int32_t max_neighbors; /* 0 -> global system (maxneighbors === nothing, krig.jl:151), else the CLAMPED k */
+  double ball_radius;    /* NaN -> KNearestSearch; else KBallSearch: kNN then dist <= radius */
+
+  uint32_t flags;
+} gsk_problem;
+
+typedef struct gsk_ctx gsk_ctx; /* opaque: one CUDA device, its stream, resident buffers */
+
+/* per-phase device times (CUDA events on the context stream) of the last gsk_execute/gsk_krige */
+typedef struct gsk_timing {
+  double ms_plan;    /* H2D of samples + bin build, or global assembly + factorisation */
+  double ms_search;  /* local: neighbour-search kernel(s) */
+  double ms_solve;   /* local: assemble+factor+solve kernel; global: RHS + triangular-solve kernels */
+  double ms_total;   /* first launch -> last result byte in the device output buffers */
+  int64_t launches;  /* kernels launched by the last gsk_execute */
+  int64_t targets;   /* targets computed by the last gsk_execute */
+} gsk_timing;
+
+/* ---- context ---------------------------------------------------------------------- */
+int gsk_create(gsk_ctx **out, int device_id);
+void gsk_destroy(gsk_ctx *ctx);
+/* NUL-terminated, owned by ctx (or static when ctx == NULL), valid until the next call on ctx */
+const char *gsk_last_error(const gsk_ctx *ctx);
+/* run all work of this context on the caller's CUDA stream (cudaStream_t passed as void*) */
+int gsk_set_stream(gsk_ctx *ctx, void *cuda_stream);
+int gsk_synchronize(gsk_ctx *ctx);
+
+/* ---- one-shot, host buffers: replaces exactsolve / approxsolve (krig.jl:166,188) --- */
+int gsk_krige(gsk_ctx *ctx, const gsk_problem *prob,
+              double *mean_out, double *var_out, /* length = slab target count */
+              int32_t *nneigh_out,               /* optional: neighbours used per target (global: n_samples) */
+              int32_t *neigh_idx_out);           /* optional: count × max_neighbors, 0-based, sorted by (d², idx), −1 padded */
+
+/* ---- resident two-step form: replaces preprocess' searcher/estimator construction
+ *      (krig.jl:110,117; fit at krig.jl:176) and then the per-target loops ------------- */
+/* uploads samples, builds the bin structure (local) or assembles + factorises the
+ * global system (max_neighbors == 0); keeps everything resident in HBM */
+int gsk_plan(gsk_ctx *ctx, const gsk_problem *prob);
+/* computes targets [first, first+count) of the planned problem into DEVICE buffers;
+ * asynchronous on the context stream */
+int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count,
+                double *d_mean, double *d_var, int32_t *d_nneigh, int32_t *d_neigh_idx);
+int gsk_get_timing(const gsk_ctx *ctx, gsk_timing *out);
+
+/* ---- host helpers shared by every binding ------------------------------------------ */
+/* number of targets of the problem's domain (grid product or n_points) */
+int64_t gsk_num_targets(const gsk_problem *prob);
+/* Universal-Kriging monomial exponents in the reference's order (GeoStatsModels UKexps:
+ * descending max exponent, stable, constant term last). out: dim × nterms, term-major
+ * (out[t*dim + d]); returns nterms or a negative error */
+int gsk_uk_exponents(int degree, int dim, int32_t *out, int out_capacity_terms);
+/* default block support of a grid cell: per axis
+ * n = ceil(side / (min(range, min side)/3)), offsets (j/(n+1) − 1/2)·side, j = 1..n.
+ * Writes x-fastest tensor-product offsets; returns n_support or a negative error */
+int gsk_default_support(int dim, const double *spacing, double vario_range,
+                        double *off_x, double *off_y, double *off_z, int capacity);
+/* measured FP64 peaks of the context's device (roofline denominators): a dependent-free
+ * DFMA loop and an mma.sync m8n8k4 f64 (DMMA) loop, TFLOP/s */
+int gsk_measure_fp64_peak(gsk_ctx *ctx, double *dfma_tflops, double *dmma_tflops);
+int gsk_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSKRIGE_H */

@@ -1,0 +1,591 @@
+/*
+ * gsk_oracle.c — CPU restatement of GeoStatsSolvers.jl's Kriging estimation path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT. Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it. libgskrige.so never links
+ * or calls it; the product has no CPU path.
+ *
+ * PARITY STATUS: *partially pinned*. The control flow restated here is the reference's
+ * (src/estimation/krig.jl:166-234, src/ui.jl:11-50) and is checked against every
+ * known-answer test the reference holds for this path (test/estimation/krig.jl:35-37,
+ * 50-52,70-72; test/ui.jl:7-37) in tests/test_oracle_reference_checks.py. The arithmetic
+ * itself lives in un-vendored Julia dependencies that are absent from /root/reference and
+ * cannot be run here (no julia binary): GeoStatsModels 0.2, Variography 0.22, Meshes 0.37
+ * (+NearestNeighbors), per ref Project.toml:25-43. Their published algorithms are restated
+ * below; each [3P] behaviour is a run-time switch in gsk_problem (support offsets, Gaussian
+ * nugget epsilon, variance clamp, sqrt round trip). Beyond the reference's nine atol=1e-3
+ * checks, numerical parity with the Julia stack is UNPINNED.
+ * A second, independent restatement (oracle/numpy_twin.py, LAPACK dsytrf/dpotrf as Julia's
+ * bunchkaufman/cholesky would call) cross-checks this file.
+ *
+ * Build: make -C oracle   (gcc -O2 -fopenmp -ffp-contract=off; no FMA contraction so that
+ * squared distances are bit-identical to the CUDA search kernel's __dmul_rn/__dadd_rn chain).
+ */
+#include "gsk_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * variogram models — Variography 0.22 [3P], SURVEY §8a a14
+ *   Gaussian     γ(h) = (s−n')(1 − exp(−3 (h/r)²)) + (h>0) n',  n' = n + eps (eps = 1e-6)
+ *   Spherical    γ(h) = (s−n)(1.5 (h/r) − 0.5 (h/r)³) for h<r, (s−n) otherwise, + (h>0) n
+ *   Exponential  γ(h) = (s−n)(1 − exp(−3 h/r)) + (h>0) n
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int kind;
+  double range, sill, nugget; /* nugget already includes the Gaussian epsilon */
+} vario_t;
+
+static vario_t vario_from(const gsk_problem *p) {
+  vario_t v;
+  v.kind = p->vario_kind;
+  v.range = p->vario_range;
+  v.sill = p->vario_sill;
+  v.nugget = p->vario_nugget + (p->vario_kind == GSK_VARIO_GAUSSIAN ? p->gaussian_nugget_eps : 0.0);
+  return v;
+}
+
+static double vario_eval(const vario_t *v, double h) {
+  double s = v->sill, n = v->nugget, r = v->range;
+  double g;
+  switch (v->kind) {
+  case GSK_VARIO_GAUSSIAN: {
+    double t = h / r;
+    g = (s - n) * (1.0 - exp(-3.0 * (t * t)));
+    break;
+  }
+  case GSK_VARIO_SPHERICAL: {
+    double t = h / r;
+    g = (h < r) ? (s - n) * (1.5 * t - 0.5 * (t * t * t)) : (s - n);
+    break;
+  }
+  default: { /* exponential */
+    g = (s - n) * (1.0 - exp(-3.0 * (h / r)));
+    break;
+  }
+  }
+  return g + ((h > 0.0) ? n : 0.0);
+}
+
+/* Squared Euclidean distance, summed left to right without FMA. The CUDA search kernel
+ * evaluates exactly this chain so that neighbour sets are bit-identical (north_star). */
+static inline double dist2(int dim, const double *a, const double *b) {
+  double d0 = a[0] - b[0];
+  double s = d0 * d0;
+  if (dim > 1) { double d1 = a[1] - b[1]; s = s + d1 * d1; }
+  if (dim > 2) { double d2 = a[2] - b[2]; s = s + d2 * d2; }
+  return s;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * targets — Meshes `centroid(grid, ind)` [3P], SURVEY V9: origin + (ijk − ½)·spacing with a
+ * column-major (x fastest) linear index (pinned by ref test/estimation/krig.jl:34-37,69-72).
+ * Stated here with a 0-based index: origin + (i + 0.5)·spacing.
+ * ---------------------------------------------------------------------------------------- */
+int64_t gsk_oracle_num_targets(const gsk_problem *p) {
+  if (p->grid_dims[0] > 0) {
+    int64_t t = 1;
+    for (int d = 0; d < p->dim; d++) t *= p->grid_dims[d];
+    return t;
+  }
+  return p->n_points;
+}
+
+static void target_center(const gsk_problem *p, int64_t lin, double *c) {
+  c[0] = c[1] = c[2] = 0.0;
+  if (p->grid_dims[0] > 0) {
+    int64_t rem = lin;
+    for (int d = 0; d < p->dim; d++) {
+      int64_t i = rem % p->grid_dims[d];
+      rem /= p->grid_dims[d];
+      c[d] = p->grid_origin[d] + ((double)i + 0.5) * p->grid_spacing[d];
+    }
+  } else {
+    for (int d = 0; d < p->dim; d++) c[d] = p->point_coords[d][lin];
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * neighbour search — Meshes KNearestSearch / KBallSearch `search!` (ref krig.jl:210) [3P]:
+ * the k nearest samples sorted ascending by distance; ball variant keeps dist <= radius.
+ * Ties are ordered by sample index (north_star).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { double d2; int32_t idx; } cand_t;
+
+static inline int cand_less(double d2a, int32_t ia, double d2b, int32_t ib) {
+  return d2a < d2b || (d2a == d2b && ia < ib);
+}
+
+/* insert into an ascending list of at most k */
+static inline void topk_insert(cand_t *best, int *cnt, int k, double d2, int32_t idx) {
+  int n = *cnt;
+  if (n == k && !cand_less(d2, idx, best[n - 1].d2, best[n - 1].idx)) return;
+  int pos = (n < k) ? n : k - 1;
+  while (pos > 0 && cand_less(d2, idx, best[pos - 1].d2, best[pos - 1].idx)) {
+    best[pos] = best[pos - 1];
+    pos--;
+  }
+  best[pos].d2 = d2;
+  best[pos].idx = idx;
+  if (n < k) *cnt = n + 1;
+}
+
+static int knn_brute(const gsk_problem *p, const double *xyz /* n×3 AoS */, const double *c, int k, cand_t *best) {
+  int cnt = 0;
+  for (int64_t i = 0; i < p->n_samples; i++) topk_insert(best, &cnt, k, dist2(p->dim, c, xyz + 3 * i), (int32_t)i);
+  return cnt;
+}
+
+/* KD-tree: median split on the widest axis, leaves of <= LEAF points. Stands in for
+ * NearestNeighbors.jl's KDTree [3P]; result is identical to brute force by construction
+ * (subtrees are pruned only when strictly farther than the current k-th candidate). */
+#define KD_LEAF 12
+typedef struct {
+  int32_t lo, hi;  /* range in perm */
+  int32_t left, right; /* children, −1 for leaf */
+  int32_t axis;
+  double split;
+} kdnode_t;
+typedef struct {
+  kdnode_t *nodes;
+  int32_t nnodes;
+  int32_t *perm;
+  const double *xyz;
+  int dim;
+} kdtree_t;
+
+static const double *g_sort_xyz;
+static int g_sort_axis;
+static int cmp_axis(const void *a, const void *b) {
+  double xa = g_sort_xyz[3 * (int64_t)(*(const int32_t *)a) + g_sort_axis];
+  double xb = g_sort_xyz[3 * (int64_t)(*(const int32_t *)b) + g_sort_axis];
+  return (xa > xb) - (xa < xb);
+}
+
+static int32_t kd_build(kdtree_t *t, int32_t lo, int32_t hi) {
+  int32_t id = t->nnodes++;
+  kdnode_t *nd = &t->nodes[id];
+  nd->lo = lo; nd->hi = hi; nd->left = nd->right = -1; nd->axis = 0; nd->split = 0;
+  if (hi - lo <= KD_LEAF) return id;
+  double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int32_t i = lo; i < hi; i++)
+    for (int d = 0; d < t->dim; d++) {
+      double v = t->xyz[3 * (int64_t)t->perm[i] + d];
+      if (v < mn[d]) mn[d] = v;
+      if (v > mx[d]) mx[d] = v;
+    }
+  int ax = 0;
+  for (int d = 1; d < t->dim; d++) if (mx[d] - mn[d] > mx[ax] - mn[ax]) ax = d;
+  if (!(mx[ax] > mn[ax])) return id; /* all points coincide: keep as a (large) leaf */
+  g_sort_xyz = t->xyz; g_sort_axis = ax;
+  qsort(t->perm + lo, (size_t)(hi - lo), sizeof(int32_t), cmp_axis);
+  int32_t mid = lo + (hi - lo) / 2;
+  double split = t->xyz[3 * (int64_t)t->perm[mid] + ax];
+  /* move mid so that everything left is strictly < split where possible */
+  while (mid > lo && t->xyz[3 * (int64_t)t->perm[mid - 1] + ax] == split) mid--;
+  if (mid == lo) { /* fall back: first index with value > split */
+    mid = lo + (hi - lo) / 2;
+    while (mid < hi && t->xyz[3 * (int64_t)t->perm[mid] + ax] == split) mid++;
+    if (mid == hi) return id;
+    split = t->xyz[3 * (int64_t)t->perm[mid] + ax];
+  }
+  int32_t l = kd_build(t, lo, mid);
+  int32_t r = kd_build(t, mid, hi);
+  nd = &t->nodes[id]; /* nodes array is preallocated, pointer stays valid */
+  nd->axis = ax; nd->split = split; nd->left = l; nd->right = r;
+  return id;
+}
+
+static kdtree_t *kd_create(const double *xyz, int64_t n, int dim) {
+  kdtree_t *t = (kdtree_t *)calloc(1, sizeof(kdtree_t));
+  t->xyz = xyz; t->dim = dim;
+  t->perm = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+  for (int64_t i = 0; i < n; i++) t->perm[i] = (int32_t)i;
+  t->nodes = (kdnode_t *)malloc(sizeof(kdnode_t) * (size_t)(2 * n + 2));
+  t->nnodes = 0;
+  kd_build(t, 0, (int32_t)n);
+  return t;
+}
+static void kd_free(kdtree_t *t) { if (t) { free(t->perm); free(t->nodes); free(t); } }
+
+static void kd_query(const kdtree_t *t, int32_t id, const double *c, int k, cand_t *best, int *cnt) {
+  const kdnode_t *nd = &t->nodes[id];
+  if (nd->left < 0) {
+    for (int32_t i = nd->lo; i < nd->hi; i++) {
+      int32_t s = t->perm[i];
+      topk_insert(best, cnt, k, dist2(t->dim, c, t->xyz + 3 * (int64_t)s), s);
+    }
+    return;
+  }
+  double diff = c[nd->axis] - nd->split;
+  int32_t near = diff < 0 ? nd->left : nd->right;
+  int32_t far = diff < 0 ? nd->right : nd->left;
+  kd_query(t, near, c, k, best, cnt);
+  /* (c−split)² is a lower bound of the computed d² of every point on the far side
+   * (rounded subtraction and addition are monotone); prune only when strictly farther */
+  double pd = diff * diff;
+  if (*cnt < k || !(pd > best[*cnt - 1].d2)) kd_query(t, far, c, k, best, cnt);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Universal Kriging monomials — GeoStatsModels UKexps [3P], SURVEY V4: all exponent vectors
+ * of total degree 0..degree (per degree in lexicographically descending order, as
+ * Combinatorics.multiexponents yields them), stably sorted by descending max exponent.
+ * degree 1 → [x, y, (z), 1];  degree 2 in 2-D → [x², y², x, y, xy, 1].
+ * ---------------------------------------------------------------------------------------- */
+int gsk_oracle_uk_exponents(int degree, int dim, int32_t *out, int cap) {
+  if (degree < 0 || degree > 2 || dim < 1 || dim > 3) return -1;
+  int32_t tmp[16][3];
+  int n = 0;
+  for (int d = 0; d <= degree; d++) {
+    /* multiexponents(dim, d): descending lexicographic */
+    for (int a = d; a >= 0; a--) {
+      if (dim == 1) { if (a == d) { tmp[n][0] = a; tmp[n][1] = tmp[n][2] = 0; n++; } continue; }
+      for (int b = d - a; b >= 0; b--) {
+        int c = d - a - b;
+        if (dim == 2) { if (c == 0) { tmp[n][0] = a; tmp[n][1] = b; tmp[n][2] = 0; n++; } continue; }
+        tmp[n][0] = a; tmp[n][1] = b; tmp[n][2] = c; n++;
+      }
+    }
+  }
+  if (n > cap) return -1;
+  int k = 0;
+  for (int mx = degree; mx >= 0; mx--)
+    for (int i = 0; i < n; i++) {
+      int m = tmp[i][0];
+      if (tmp[i][1] > m) m = tmp[i][1];
+      if (tmp[i][2] > m) m = tmp[i][2];
+      if (m == mx) { for (int d = 0; d < dim; d++) out[k * dim + d] = tmp[i][d]; k++; }
+    }
+  return n;
+}
+
+static double monomial(int dim, const int32_t *e, const double *x) {
+  double v = 1.0;
+  for (int d = 0; d < dim; d++)
+    for (int q = 0; q < e[d]; q++) v *= x[d];
+  return v;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * dense factorisations (column-major, leading dimension m)
+ *   lu_factor / lu_solve     : partial-pivot LU. Stands in for Julia's bunchkaufman(Symmetric(LHS),
+ *                              check=false) on the OK/UK systems [3P, V3] — same solution up to rounding
+ *                              (numpy_twin.py does call LAPACK dsytrf and pins the difference).
+ *   chol_factor / chol_solve : Cholesky for Simple Kriging (Julia: cholesky(Symmetric(LHS), check=false)).
+ * A zero pivot is not an error (check=false): the division produces Inf/NaN that flow to the output.
+ * ---------------------------------------------------------------------------------------- */
+static void lu_factor(int m, double *A, int32_t *piv) {
+  for (int j = 0; j < m; j++) {
+    int p = j;
+    double best = fabs(A[j + (size_t)j * m]);
+    for (int i = j + 1; i < m; i++) {
+      double v = fabs(A[i + (size_t)j * m]);
+      if (v > best) { best = v; p = i; }
+    }
+    piv[j] = p;
+    if (p != j)
+      for (int c = 0; c < m; c++) {
+        double t = A[j + (size_t)c * m];
+        A[j + (size_t)c * m] = A[p + (size_t)c * m];
+        A[p + (size_t)c * m] = t;
+      }
+    double d = A[j + (size_t)j * m];
+    for (int i = j + 1; i < m; i++) A[i + (size_t)j * m] /= d;
+    for (int c = j + 1; c < m; c++) {
+      double u = A[j + (size_t)c * m];
+      if (u != 0.0)
+        for (int i = j + 1; i < m; i++) A[i + (size_t)c * m] -= A[i + (size_t)j * m] * u;
+    }
+  }
+}
+static void lu_solve(int m, const double *A, const int32_t *piv, double *b) {
+  for (int j = 0; j < m; j++) {
+    int p = piv[j];
+    if (p != j) { double t = b[j]; b[j] = b[p]; b[p] = t; }
+  }
+  for (int j = 0; j < m; j++) {
+    double v = b[j];
+    if (v != 0.0)
+      for (int i = j + 1; i < m; i++) b[i] -= A[i + (size_t)j * m] * v;
+  }
+  for (int j = m - 1; j >= 0; j--) {
+    b[j] /= A[j + (size_t)j * m];
+    double v = b[j];
+    for (int i = 0; i < j; i++) b[i] -= A[i + (size_t)j * m] * v;
+  }
+}
+static void chol_factor(int m, double *A) { /* lower */
+  for (int j = 0; j < m; j++) {
+    double d = A[j + (size_t)j * m];
+    for (int p = 0; p < j; p++) d -= A[j + (size_t)p * m] * A[j + (size_t)p * m];
+    d = sqrt(d);
+    A[j + (size_t)j * m] = d;
+    for (int i = j + 1; i < m; i++) {
+      double s = A[i + (size_t)j * m];
+      for (int p = 0; p < j; p++) s -= A[i + (size_t)p * m] * A[j + (size_t)p * m];
+      A[i + (size_t)j * m] = s / d;
+    }
+  }
+}
+static void chol_solve(int m, const double *A, double *b) {
+  for (int j = 0; j < m; j++) {
+    double s = b[j];
+    for (int p = 0; p < j; p++) s -= A[j + (size_t)p * m] * b[p];
+    b[j] = s / A[j + (size_t)j * m];
+  }
+  for (int j = m - 1; j >= 0; j--) {
+    double s = b[j];
+    for (int p = j + 1; p < m; p++) s -= A[p + (size_t)j * m] * b[p];
+    b[j] = s / A[j + (size_t)j * m];
+  }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * GeoStatsModels.fit [3P] (ref krig.jl:176,223), SURVEY §8a a13: LHS of the kriging system for
+ * the k samples `nb` in covariance form (sill − γ), plus constraint blocks, then factorise.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int k, c, m;
+  double *A;     /* m×m factor */
+  int32_t *piv;  /* LU pivots (OK/UK) */
+} fitted_t;
+
+static int n_constraints(const gsk_problem *p, int32_t *exps) {
+  if (p->estimator == GSK_EST_SIMPLE) return 0;
+  if (p->estimator == GSK_EST_ORDINARY) return 1;
+  return gsk_oracle_uk_exponents(p->uk_degree, p->dim, exps, GSK_MAX_DRIFT_TERMS);
+}
+
+static void fit_system(const gsk_problem *p, const vario_t *v, const double *xyz, const int32_t *nb, int k,
+                       int c, const int32_t *exps, fitted_t *f) {
+  int m = k + c;
+  f->k = k; f->c = c; f->m = m;
+  double *A = f->A;
+  /* Variography.pairwise!: Γij = γ(‖xi − xj‖), diagonal γ(0) = 0; stationary γ → C = sill − Γ */
+  for (int j = 0; j < k; j++) {
+    A[j + (size_t)j * m] = v->sill - vario_eval(v, 0.0);
+    for (int i = j + 1; i < k; i++) {
+      double h = sqrt(dist2(p->dim, xyz + 3 * (int64_t)nb[i], xyz + 3 * (int64_t)nb[j]));
+      double cij = v->sill - vario_eval(v, h);
+      A[i + (size_t)j * m] = cij;
+      A[j + (size_t)i * m] = cij;
+    }
+  }
+  if (p->estimator == GSK_EST_ORDINARY) {
+    for (int i = 0; i < k; i++) { A[k + (size_t)i * m] = 1.0; A[i + (size_t)k * m] = 1.0; }
+    A[k + (size_t)k * m] = 0.0;
+  } else if (p->estimator == GSK_EST_UNIVERSAL) {
+    for (int i = 0; i < k; i++)
+      for (int t = 0; t < c; t++) {
+        double f_it = monomial(p->dim, exps + t * p->dim, xyz + 3 * (int64_t)nb[i]);
+        A[(k + t) + (size_t)i * m] = f_it;
+        A[i + (size_t)(k + t) * m] = f_it;
+      }
+    for (int a = 0; a < c; a++)
+      for (int b = 0; b < c; b++) A[(k + a) + (size_t)(k + b) * m] = 0.0;
+  }
+  if (p->estimator == GSK_EST_SIMPLE) chol_factor(m, A);
+  else lu_factor(m, A, f->piv);
+}
+
+/* GeoStatsModels.predictprob [3P] (ref krig.jl:180,226), SURVEY §8a a15-a16 */
+static void predict(const gsk_problem *p, const vario_t *v, const double *xyz, const int32_t *nb,
+                    const fitted_t *f, const int32_t *exps, const double *center, double *rhs, double *sol,
+                    double *mean_out, double *var_out) {
+  int k = f->k, c = f->c, m = f->m;
+  int q = p->n_support;
+  for (int j = 0; j < k; j++) {
+    /* γ(U, xj) with U the target geometry: arithmetic mean over its sub-sample points */
+    double acc = 0.0;
+    for (int s = 0; s < q; s++) {
+      double u[3] = {center[0], center[1], center[2]};
+      for (int d = 0; d < p->dim; d++) u[d] = center[d] + (p->support_offsets[d] ? p->support_offsets[d][s] : 0.0);
+      double h = sqrt(dist2(p->dim, u, xyz + 3 * (int64_t)nb[j]));
+      acc += vario_eval(v, h);
+    }
+    rhs[j] = v->sill - acc / (double)q;
+  }
+  if (p->estimator == GSK_EST_ORDINARY) rhs[k] = 1.0;
+  else if (p->estimator == GSK_EST_UNIVERSAL)
+    for (int t = 0; t < c; t++) rhs[k + t] = monomial(p->dim, exps + t * p->dim, center);
+  memcpy(sol, rhs, sizeof(double) * (size_t)m);
+  if (p->estimator == GSK_EST_SIMPLE) chol_solve(m, f->A, sol);
+  else lu_solve(m, f->A, f->piv, sol);
+  /* mean */
+  double mu = 0.0;
+  if (p->estimator == GSK_EST_SIMPLE) {
+    for (int i = 0; i < k; i++) mu += sol[i] * (p->values[nb[i]] - p->sk_mean);
+    mu = p->sk_mean + mu;
+  } else {
+    for (int i = 0; i < k; i++) mu += sol[i] * p->values[nb[i]];
+  }
+  /* variance: sill − b·[λ;ν], clamped, then the Normal(μ,√σ²) → var() round trip */
+  double c1 = 0.0, c2 = 0.0;
+  for (int i = 0; i < k; i++) c1 += rhs[i] * sol[i];
+  for (int i = k; i < m; i++) c2 += rhs[i] * sol[i];
+  double s2 = v->sill - (c1 + c2);
+  if (p->flags & GSK_FLAG_CLAMP_VARIANCE) s2 = (s2 > 0.0 || s2 != s2) ? s2 : 0.0;
+  if (p->flags & GSK_FLAG_SQRT_ROUNDTRIP) { double sd = sqrt(s2); s2 = sd * sd; }
+  *mean_out = mu;
+  *var_out = s2;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * entry point: exactsolve (krig.jl:166-186) when max_neighbors == 0, approxsolve
+ * (krig.jl:188-234) otherwise, over the slab [target_first, target_first+target_count).
+ * ---------------------------------------------------------------------------------------- */
+int gsk_oracle_krige(const gsk_problem *p, double *mean_out, double *var_out, int32_t *nneigh_out,
+                     int32_t *neigh_idx_out, int search_kind, int nthreads) {
+  if (!p || p->dim < 1 || p->dim > 3 || p->n_samples < 1 || p->n_support < 1) return GSK_ERR_INVALID;
+  int64_t T = gsk_oracle_num_targets(p);
+  int64_t first = p->target_first;
+  int64_t count = p->target_count < 0 ? T - first : p->target_count;
+  if (first < 0 || first + count > T) return GSK_ERR_INVALID;
+  int64_t n = p->n_samples;
+  int dim = p->dim;
+  vario_t v = vario_from(p);
+  int32_t exps[3 * GSK_MAX_DRIFT_TERMS];
+  int c = n_constraints(p, exps);
+  if (c < 0) return GSK_ERR_INVALID;
+
+  double *xyz = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+  for (int64_t i = 0; i < n; i++)
+    for (int d = 0; d < 3; d++) xyz[3 * i + d] = (d < dim) ? p->coords[d][i] : 0.0;
+
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+  (void)nthreads;
+#endif
+
+  if (p->max_neighbors == 0) {
+    /* ---- exactsolve: fit once on all samples, predict everywhere (krig.jl:176-180) ---- */
+    int m = (int)n + c;
+    fitted_t f;
+    f.A = (double *)malloc(sizeof(double) * (size_t)m * m);
+    f.piv = (int32_t *)malloc(sizeof(int32_t) * (size_t)m);
+    int32_t *nb = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+    for (int64_t i = 0; i < n; i++) nb[i] = (int32_t)i;
+    fit_system(p, &v, xyz, nb, (int)n, c, exps, &f);
+#pragma omp parallel
+    {
+      double *rhs = (double *)malloc(sizeof(double) * (size_t)m);
+      double *sol = (double *)malloc(sizeof(double) * (size_t)m);
+#pragma omp for schedule(dynamic, 16)
+      for (int64_t t = 0; t < count; t++) {
+        double ctr[3];
+        target_center(p, first + t, ctr);
+        predict(p, &v, xyz, nb, &f, exps, ctr, rhs, sol, &mean_out[t], &var_out[t]);
+        if (nneigh_out) nneigh_out[t] = (int32_t)n;
+      }
+      free(rhs); free(sol);
+    }
+    free(nb); free(f.A); free(f.piv);
+    free(xyz);
+    return GSK_OK;
+  }
+
+  /* ---- approxsolve: per target search → fit → predict (krig.jl:205-228) ---- */
+  int k = p->max_neighbors;
+  if (k < 1 || k > n) { free(xyz); return GSK_ERR_INVALID; } /* host clamps first (ui.jl:16-23) */
+  kdtree_t *tree = (search_kind == GSK_ORACLE_SEARCH_KDTREE) ? kd_create(xyz, n, dim) : NULL;
+  int use_ball = !(p->ball_radius != p->ball_radius);
+  int mmax = k + c;
+#pragma omp parallel
+  {
+    cand_t *best = (cand_t *)malloc(sizeof(cand_t) * (size_t)k);
+    int32_t *nb = (int32_t *)malloc(sizeof(int32_t) * (size_t)k);
+    fitted_t f;
+    f.A = (double *)malloc(sizeof(double) * (size_t)mmax * mmax);
+    f.piv = (int32_t *)malloc(sizeof(int32_t) * (size_t)mmax);
+    double *rhs = (double *)malloc(sizeof(double) * (size_t)mmax);
+    double *sol = (double *)malloc(sizeof(double) * (size_t)mmax);
+#pragma omp for schedule(dynamic, 64)
+    for (int64_t t = 0; t < count; t++) {
+      double ctr[3];
+      target_center(p, first + t, ctr); /* centroid(pdomain, ind), krig.jl:207 */
+      int cnt = 0;
+      if (tree) kd_query(tree, 0, ctr, k, best, &cnt);
+      else cnt = knn_brute(p, xyz, ctr, k, best);
+      int nn = cnt;
+      if (use_ball) { /* KBallSearch: keep dists .<= radius (inclusive) */
+        nn = 0;
+        while (nn < cnt && sqrt(best[nn].d2) <= p->ball_radius) nn++;
+      }
+      for (int i = 0; i < nn; i++) nb[i] = best[i].idx;
+      if (nneigh_out) nneigh_out[t] = nn;
+      if (neigh_idx_out)
+        for (int i = 0; i < k; i++) neigh_idx_out[t * (int64_t)k + i] = (i < nn) ? nb[i] : -1;
+      if (nn < p->min_neighbors || nn == 0) { /* krig.jl:213-214 → (missing, missing) */
+        mean_out[t] = NAN;
+        var_out[t] = NAN;
+        continue;
+      }
+      fit_system(p, &v, xyz, nb, nn, c, exps, &f);
+      predict(p, &v, xyz, nb, &f, exps, ctr, rhs, sol, &mean_out[t], &var_out[t]);
+    }
+    free(best); free(nb); free(f.A); free(f.piv); free(rhs); free(sol);
+  }
+  kd_free(tree);
+  free(xyz);
+  return GSK_OK;
+}
+
+/* search only (for neighbour-set parity tests) */
+int gsk_oracle_search(const gsk_problem *p, int32_t *nneigh_out, int32_t *neigh_idx_out, double *d2_out,
+                      int search_kind, int nthreads) {
+  if (!p || p->max_neighbors < 1 || p->max_neighbors > p->n_samples) return GSK_ERR_INVALID;
+  int64_t T = gsk_oracle_num_targets(p);
+  int64_t first = p->target_first;
+  int64_t count = p->target_count < 0 ? T - first : p->target_count;
+  if (first < 0 || first + count > T) return GSK_ERR_INVALID;
+  int64_t n = p->n_samples;
+  int k = p->max_neighbors;
+  double *xyz = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+  for (int64_t i = 0; i < n; i++)
+    for (int d = 0; d < 3; d++) xyz[3 * i + d] = (d < p->dim) ? p->coords[d][i] : 0.0;
+  kdtree_t *tree = (search_kind == GSK_ORACLE_SEARCH_KDTREE) ? kd_create(xyz, n, p->dim) : NULL;
+  int use_ball = !(p->ball_radius != p->ball_radius);
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+  (void)nthreads;
+#endif
+#pragma omp parallel
+  {
+    cand_t *best = (cand_t *)malloc(sizeof(cand_t) * (size_t)k);
+#pragma omp for schedule(dynamic, 64)
+    for (int64_t t = 0; t < count; t++) {
+      double ctr[3];
+      target_center(p, first + t, ctr);
+      int cnt = 0;
+      if (tree) kd_query(tree, 0, ctr, k, best, &cnt);
+      else cnt = knn_brute(p, xyz, ctr, k, best);
+      int nn = cnt;
+      if (use_ball) { nn = 0; while (nn < cnt && sqrt(best[nn].d2) <= p->ball_radius) nn++; }
+      if (nneigh_out) nneigh_out[t] = nn;
+      for (int i = 0; i < k; i++) {
+        if (neigh_idx_out) neigh_idx_out[t * (int64_t)k + i] = (i < nn) ? best[i].idx : -1;
+        if (d2_out) d2_out[t * (int64_t)k + i] = (i < nn) ? best[i].d2 : NAN;
+      }
+    }
+    free(best);
+  }
+  kd_free(tree);
+  free(xyz);
+  return GSK_OK;
+}
+
+int gsk_oracle_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
