@@ -1,0 +1,445 @@
+// api.cu — the C ABI of libgskrige.so (include/gskrige.h): context, plan/execute orchestration, the
+// one-shot host-buffer entry point that replaces exactsolve/approxsolve (ref: src/estimation/krig.jl:
+// 166-186, 188-234), and the host helpers every binding shares. No CPU compute path exists here:
+// without an sm_100 device gsk_create fails and nothing else can be called.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "gsk_internal.cuh"
+
+static thread_local std::string g_static_err;
+
+static int fail(gsk_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg;
+  else g_static_err = msg;
+  return code;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------------------------
+extern "C" int gsk_abi_version(void) { return GSK_ABI_VERSION; }
+
+extern "C" int64_t gsk_num_targets(const gsk_problem *p) {
+  if (!p) return -1;
+  if (p->grid_dims[0] > 0) {
+    int64_t t = 1;
+    for (int d = 0; d < p->dim && d < 3; ++d) t *= p->grid_dims[d];
+    return t;
+  }
+  return p->n_points;
+}
+
+// GeoStatsModels' UKexps [3P]: exponent vectors of total degree 0..degree (each degree in descending
+// lexicographic order), stably sorted by descending max exponent → degree 1: x, y, (z), 1.
+extern "C" int gsk_uk_exponents(int degree, int dim, int32_t *out, int cap) {
+  if (degree < 0 || degree > 2 || dim < 1 || dim > 3 || !out) return GSK_ERR_INVALID;
+  int tmp[16][3];
+  int n = 0;
+  for (int deg = 0; deg <= degree; ++deg)
+    for (int a = deg; a >= 0; --a)
+      for (int b = deg - a; b >= 0; --b) {
+        int c = deg - a - b;
+        if (dim == 1 && (b != 0 || c != 0)) continue;
+        if (dim == 2 && c != 0) continue;
+        tmp[n][0] = a; tmp[n][1] = b; tmp[n][2] = c;
+        ++n;
+      }
+  if (n > cap) return GSK_ERR_INVALID;
+  int w = 0;
+  for (int mx = degree; mx >= 0; --mx)
+    for (int i = 0; i < n; ++i)
+      if (std::max(tmp[i][0], std::max(tmp[i][1], tmp[i][2])) == mx) {
+        for (int d = 0; d < dim; ++d) out[w * dim + d] = tmp[i][d];
+        ++w;
+      }
+  return n;
+}
+
+// Variography's geometry sub-sampling for γ(cell, point) [3P, SURVEY V1]: per axis
+// n = ceil(side / (min(range, min side)/3)) points at parametric positions j/(n+1), j = 1..n.
+extern "C" int gsk_default_support(int dim, const double *spacing, double vario_range, double *ox, double *oy,
+                                   double *oz, int cap) {
+  if (dim < 1 || dim > 3 || !spacing || !ox) return GSK_ERR_INVALID;
+  double lmin = INFINITY;
+  for (int d = 0; d < dim; ++d)
+    if (spacing[d] > 0) lmin = std::min(lmin, spacing[d]);
+  if (!(lmin < INFINITY)) return GSK_ERR_INVALID;
+  double step = ((vario_range > 0) ? std::min(vario_range, lmin) : lmin) / 3.0;
+  int n[3] = {1, 1, 1};
+  long long tot = 1;
+  for (int d = 0; d < dim; ++d) {
+    n[d] = std::max(1, (int)ceil(spacing[d] / step - 1e-12));
+    tot *= n[d];
+  }
+  if (tot > cap) return GSK_ERR_INVALID;
+  double *o[3] = {ox, oy, oz};
+  int w = 0;
+  for (int kz = 0; kz < n[2]; ++kz)
+    for (int ky = 0; ky < n[1]; ++ky)
+      for (int kx = 0; kx < n[0]; ++kx) {
+        int kk[3] = {kx, ky, kz};
+        for (int d = 0; d < dim; ++d)
+          if (o[d]) o[d][w] = ((double)(kk[d] + 1) / (double)(n[d] + 1) - 0.5) * spacing[d];
+        ++w;
+      }
+  return (int)tot;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+extern "C" int gsk_create(gsk_ctx **out, int device_id) {
+  if (!out) return fail(nullptr, GSK_ERR_INVALID, "gsk_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, GSK_ERR_CUDA,
+                std::string("no CUDA device visible (libgskrige has no CPU fallback): ") + cudaGetErrorString(e));
+  if (device_id < 0 || device_id >= ndev) return fail(nullptr, GSK_ERR_INVALID, "gsk_create: device_id out of range");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device_id);
+  if (e != cudaSuccess) return fail(nullptr, GSK_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, GSK_ERR_CUDA, "device is not sm_100 (libgskrige is built for B200 / sm_100a only)");
+  gsk_ctx *ctx = new (std::nothrow) gsk_ctx();
+  if (!ctx) return fail(nullptr, GSK_ERR_NOMEM, "gsk_create: out of host memory");
+  ctx->device = device_id;
+  ctx->sm_count = prop.multiProcessorCount;
+  e = cudaSetDevice(device_id);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  ctx->own_stream = true;
+  for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+  if (e != cudaSuccess) {
+    std::string m = cudaGetErrorString(e);
+    delete ctx;
+    return fail(nullptr, GSK_ERR_CUDA, m);
+  }
+  *out = ctx;
+  return GSK_OK;
+}
+
+static void free_plan(gsk_ctx *ctx) {
+  cudaFree(ctx->d_rec_orig); ctx->d_rec_orig = nullptr;
+  cudaFree(ctx->d_rec_sorted); ctx->d_rec_sorted = nullptr;
+  cudaFree(ctx->d_cell_start); ctx->d_cell_start = nullptr;
+  cudaFree(ctx->d_sup); ctx->d_sup = nullptr;
+  for (int d = 0; d < 3; ++d) { cudaFree(ctx->d_pts[d]); ctx->d_pts[d] = nullptr; }
+  gsk_global_free(ctx);
+  ctx->planned = false;
+}
+
+extern "C" void gsk_destroy(gsk_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  free_plan(ctx);
+  cudaFree(ctx->d_nn);
+  cudaFree(ctx->d_nbr);
+  cudaFree(ctx->d_mean);
+  cudaFree(ctx->d_var);
+  for (int i = 0; i < 6; ++i)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char *gsk_last_error(const gsk_ctx *ctx) { return ctx ? ctx->err.c_str() : g_static_err.c_str(); }
+
+extern "C" int gsk_set_stream(gsk_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return GSK_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return GSK_OK;
+}
+
+extern "C" int gsk_synchronize(gsk_ctx *ctx) {
+  if (!ctx) return GSK_ERR_INVALID;
+  GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return GSK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------------------------
+static int validate(gsk_ctx *ctx, const gsk_problem *p) {
+  if (!p) return fail(ctx, GSK_ERR_INVALID, "problem is NULL");
+  if (p->abi_version != GSK_ABI_VERSION) return fail(ctx, GSK_ERR_INVALID, "gsk_problem.abi_version mismatch");
+  if (p->dim < 1 || p->dim > 3) return fail(ctx, GSK_ERR_UNSUPPORTED, "dim must be 1, 2 or 3");
+  if (p->n_samples < 1) return fail(ctx, GSK_ERR_INVALID, "n_samples must be >= 1");
+  if (p->n_samples > 0x7fffffffLL) return fail(ctx, GSK_ERR_UNSUPPORTED, "n_samples must fit in int32");
+  if (!p->values) return fail(ctx, GSK_ERR_INVALID, "values is NULL");
+  for (int d = 0; d < p->dim; ++d)
+    if (!p->coords[d]) return fail(ctx, GSK_ERR_INVALID, "coords[d] is NULL for d < dim");
+  if (p->grid_dims[0] > 0) {
+    for (int d = 0; d < p->dim; ++d)
+      if (p->grid_dims[d] < 1) return fail(ctx, GSK_ERR_INVALID, "grid_dims must be >= 1");
+  } else {
+    if (p->n_points < 0) return fail(ctx, GSK_ERR_INVALID, "n_points must be >= 0");
+    for (int d = 0; d < p->dim; ++d)
+      if (p->n_points > 0 && !p->point_coords[d]) return fail(ctx, GSK_ERR_INVALID, "point_coords[d] is NULL");
+  }
+  if (p->n_support < 1 || p->n_support > GSK_MAX_SUPPORT)
+    return fail(ctx, GSK_ERR_INVALID, "n_support must be in [1, GSK_MAX_SUPPORT]");
+  if (p->vario_kind < 0 || p->vario_kind > 2) return fail(ctx, GSK_ERR_UNSUPPORTED, "unknown variogram kind");
+  if (!(p->vario_range > 0.0)) return fail(ctx, GSK_ERR_INVALID, "vario_range must be > 0");
+  if (!(p->vario_sill > 0.0)) return fail(ctx, GSK_ERR_INVALID, "vario_sill must be > 0");
+  if (p->estimator < 0 || p->estimator > 2) return fail(ctx, GSK_ERR_UNSUPPORTED, "unknown estimator");
+  if (p->estimator == GSK_EST_UNIVERSAL && (p->uk_degree < 0 || p->uk_degree > 2))
+    return fail(ctx, GSK_ERR_UNSUPPORTED, "uk_degree must be 0, 1 or 2");
+  if (p->max_neighbors < 0) return fail(ctx, GSK_ERR_INVALID, "max_neighbors must be >= 0");
+  if (p->max_neighbors > GSK_MAX_NEIGHBORS)
+    return fail(ctx, GSK_ERR_UNSUPPORTED, "max_neighbors exceeds GSK_MAX_NEIGHBORS on the local path");
+  if (p->max_neighbors > p->n_samples)
+    return fail(ctx, GSK_ERR_INVALID, "max_neighbors must be clamped to n_samples by the host (ui.jl:16-23)");
+  if (p->max_neighbors > 0 && !(p->ball_radius != p->ball_radius) && !(p->ball_radius > 0.0))
+    return fail(ctx, GSK_ERR_INVALID, "ball_radius must be > 0 or NaN");
+  int64_t T = gsk_num_targets(p);
+  int64_t first = p->target_first, count = p->target_count < 0 ? T - first : p->target_count;
+  if (first < 0 || count < 0 || first + count > T) return fail(ctx, GSK_ERR_INVALID, "target slab out of range");
+  return GSK_OK;
+}
+
+extern "C" int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) {
+  if (!ctx) return GSK_ERR_INVALID;
+  int rc = validate(ctx, p);
+  if (rc != GSK_OK) return rc;
+  GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  free_plan(ctx);
+  GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+  ctx->prob = *p;
+  ctx->n_targets = gsk_num_targets(p);
+  const int dim = p->dim;
+
+  // variogram constants
+  GskVario &v = ctx->vg;
+  v.kind = p->vario_kind;
+  v.sill = p->vario_sill;
+  double nug = p->vario_nugget + (p->vario_kind == GSK_VARIO_GAUSSIAN ? p->gaussian_nugget_eps : 0.0);
+  v.cs = p->vario_sill - nug;
+  v.range = p->vario_range;
+  v.inv_r = 1.0 / p->vario_range;
+  v.inv_r2 = v.inv_r * v.inv_r;
+
+  // estimator
+  GskEstimator &es = ctx->es;
+  memset(&es, 0, sizeof(es));
+  es.kind = p->estimator;
+  es.sk_mean = p->sk_mean;
+  es.nterms = 0;
+  if (p->estimator == GSK_EST_ORDINARY) es.nterms = 1;
+  if (p->estimator == GSK_EST_UNIVERSAL) {
+    int32_t ex[3 * GSK_MAX_DRIFT_TERMS];
+    int c = gsk_uk_exponents(p->uk_degree, dim, ex, GSK_MAX_DRIFT_TERMS);
+    if (c < 0) return fail(ctx, GSK_ERR_UNSUPPORTED, "unsupported Universal Kriging degree");
+    es.nterms = c;
+    for (int t = 0; t < c; ++t)
+      for (int d = 0; d < dim; ++d) es.exps[t][d] = ex[t * dim + d];
+  }
+  ctx->nterms = es.nterms;
+
+  // targets
+  GskTargets &tg = ctx->tg;
+  memset(&tg, 0, sizeof(tg));
+  tg.dim = dim;
+  tg.is_grid = p->grid_dims[0] > 0;
+  for (int d = 0; d < 3; ++d) {
+    tg.gdim[d] = (tg.is_grid && d < dim) ? p->grid_dims[d] : 1;
+    tg.gorg[d] = (d < dim) ? p->grid_origin[d] : 0.0;
+    tg.gsp[d] = (d < dim) ? p->grid_spacing[d] : 1.0;
+  }
+  if (!tg.is_grid) {
+    tg.npts = p->n_points;
+    for (int d = 0; d < dim; ++d) {
+      GSK_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_pts[d], sizeof(double) * (size_t)std::max<int64_t>(1, p->n_points)));
+      GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_pts[d], p->point_coords[d], sizeof(double) * (size_t)p->n_points,
+                                          cudaMemcpyHostToDevice, ctx->stream));
+      tg.pts[d] = ctx->d_pts[d];
+    }
+  }
+
+  // block support offsets, [3][nsup]
+  {
+    std::vector<double> sup(3 * (size_t)p->n_support, 0.0);
+    for (int d = 0; d < dim; ++d)
+      if (p->support_offsets[d])
+        for (int q = 0; q < p->n_support; ++q) sup[(size_t)d * p->n_support + q] = p->support_offsets[d][q];
+    GSK_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_sup, sizeof(double) * sup.size()));
+    GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_sup, sup.data(), sizeof(double) * sup.size(), cudaMemcpyHostToDevice,
+                                        ctx->stream));
+    GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+
+  if (p->max_neighbors > 0) {
+    rc = gsk_build_bins(ctx, p->coords[0], dim > 1 ? p->coords[1] : nullptr, dim > 2 ? p->coords[2] : nullptr,
+                        p->values, p->n_samples, dim, p->max_neighbors);
+  } else {
+    rc = gsk_global_plan(ctx, p->coords[0], dim > 1 ? p->coords[1] : nullptr, dim > 2 ? p->coords[2] : nullptr,
+                         p->values);
+  }
+  if (rc != GSK_OK) return rc;
+  GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+  ctx->timing = gsk_timing{};
+  ctx->timing.ms_plan = ms;
+  // the host pointers of the problem are not kept
+  for (int d = 0; d < 3; ++d) { ctx->prob.coords[d] = nullptr; ctx->prob.point_coords[d] = nullptr; ctx->prob.support_offsets[d] = nullptr; }
+  ctx->prob.values = nullptr;
+  ctx->planned = true;
+  return GSK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// execute
+// ---------------------------------------------------------------------------------------------
+static int ensure(gsk_ctx *ctx, void **buf, size_t *cap, size_t bytes) {
+  if (*cap >= bytes) return GSK_OK;
+  cudaFree(*buf);
+  *buf = nullptr;
+  *cap = 0;
+  cudaError_t e = cudaMalloc(buf, bytes);
+  if (e != cudaSuccess) return fail(ctx, GSK_ERR_NOMEM, std::string("device allocation failed: ") + cudaGetErrorString(e));
+  *cap = bytes;
+  return GSK_OK;
+}
+
+static long long local_chunk_targets() {
+  static long long v = 0;
+  if (!v) {
+    const char *s = getenv("GSK_CHUNK_TARGETS");
+    v = s ? atoll(s) : (1ll << 20);
+    if (v < 1024) v = 1024;
+  }
+  return v;
+}
+
+extern "C" int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count, double *d_mean, double *d_var,
+                           int32_t *d_nneigh, int32_t *d_neigh_idx) {
+  if (!ctx) return GSK_ERR_INVALID;
+  if (!ctx->planned) return fail(ctx, GSK_ERR_STATE, "gsk_execute called before gsk_plan");
+  if (first < 0 || count < 0 || first + count > ctx->n_targets) return fail(ctx, GSK_ERR_INVALID, "target range out of bounds");
+  if (!d_mean || !d_var) return fail(ctx, GSK_ERR_INVALID, "output buffers are NULL");
+  GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  static const bool phase_timing = getenv("GSK_PHASE_TIMING") != nullptr;
+  int launches = 0;
+  double ms_search = 0.0, ms_solve = 0.0;
+  GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+  int rc = GSK_OK;
+  if (ctx->prob.max_neighbors == 0) {
+    rc = gsk_global_execute(ctx, first, count, d_mean, d_var, d_nneigh, &launches);
+    if (rc != GSK_OK) return rc;
+  } else {
+    const int k = ctx->prob.max_neighbors;
+    const long long chunk = std::min<long long>(local_chunk_targets(), std::max<long long>(count, 1));
+    if (!d_nneigh) {
+      rc = ensure(ctx, (void **)&ctx->d_nn, &ctx->cap_nn, sizeof(int) * (size_t)chunk);
+      if (rc != GSK_OK) return rc;
+    }
+    if (!d_neigh_idx) {
+      rc = ensure(ctx, (void **)&ctx->d_nbr, &ctx->cap_nbr, sizeof(int) * (size_t)chunk * k);
+      if (rc != GSK_OK) return rc;
+    }
+    for (long long off = 0; off < count; off += chunk) {
+      const long long cnt = std::min<long long>(chunk, count - off);
+      int *nn = d_nneigh ? d_nneigh + off : ctx->d_nn;
+      int *nbr = d_neigh_idx ? d_neigh_idx + off * k : ctx->d_nbr;
+      if (phase_timing) cudaEventRecord(ctx->ev[3], ctx->stream);
+      rc = gsk_launch_search(ctx, first + off, cnt, nn, nbr, &launches);
+      if (rc != GSK_OK) return rc;
+      if (phase_timing) cudaEventRecord(ctx->ev[4], ctx->stream);
+      rc = gsk_launch_local_solve(ctx, first + off, cnt, nn, nbr, d_mean + off, d_var + off, &launches);
+      if (rc != GSK_OK) return rc;
+      if (phase_timing) {
+        cudaEventRecord(ctx->ev[5], ctx->stream);
+        cudaEventSynchronize(ctx->ev[5]);
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, ctx->ev[3], ctx->ev[4]);
+        cudaEventElapsedTime(&b, ctx->ev[4], ctx->ev[5]);
+        ms_search += a;
+        ms_solve += b;
+      }
+    }
+  }
+  GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+  ctx->timing.ms_search = ms_search;
+  ctx->timing.ms_solve = ms_solve;
+  ctx->timing.launches = launches;
+  ctx->timing.targets = count;
+  ctx->timing_pending = true;
+  return GSK_OK;
+}
+
+extern "C" int gsk_get_timing(const gsk_ctx *cctx, gsk_timing *out) {
+  gsk_ctx *ctx = const_cast<gsk_ctx *>(cctx);
+  if (!ctx || !out) return GSK_ERR_INVALID;
+  if (ctx->timing_pending) {
+    cudaSetDevice(ctx->device);
+    if (cudaEventSynchronize(ctx->ev[1]) == cudaSuccess) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[1]) == cudaSuccess) ctx->timing.ms_total = ms;
+    }
+    ctx->timing_pending = false;
+  }
+  *out = ctx->timing;
+  return GSK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one-shot host-buffer call: plan + execute + copies
+// ---------------------------------------------------------------------------------------------
+extern "C" int gsk_krige(gsk_ctx *ctx, const gsk_problem *p, double *mean_out, double *var_out, int32_t *nneigh_out,
+                         int32_t *neigh_idx_out) {
+  if (!ctx) return GSK_ERR_INVALID;
+  if (!mean_out || !var_out) return fail(ctx, GSK_ERR_INVALID, "mean_out / var_out are NULL");
+  int rc = gsk_plan(ctx, p);
+  if (rc != GSK_OK) return rc;
+  const int64_t T = ctx->n_targets;
+  const int64_t first = p->target_first;
+  const int64_t count = p->target_count < 0 ? T - first : p->target_count;
+  if (count == 0) return GSK_OK;
+  const int k = p->max_neighbors;
+  rc = ensure(ctx, (void **)&ctx->d_mean, &ctx->cap_out, sizeof(double) * 2 * (size_t)count);
+  if (rc != GSK_OK) return rc;
+  double *d_mean = ctx->d_mean, *d_var = ctx->d_mean + count;
+  int *d_nn = nullptr, *d_idx = nullptr;
+  if (nneigh_out) {
+    rc = ensure(ctx, (void **)&ctx->d_nn, &ctx->cap_nn, sizeof(int) * (size_t)count);
+    if (rc != GSK_OK) return rc;
+    d_nn = ctx->d_nn;
+  }
+  if (neigh_idx_out && k > 0) {
+    rc = ensure(ctx, (void **)&ctx->d_nbr, &ctx->cap_nbr, sizeof(int) * (size_t)count * k);
+    if (rc != GSK_OK) return rc;
+    d_idx = ctx->d_nbr;
+  }
+  rc = gsk_execute(ctx, first, count, d_mean, d_var, d_nn, d_idx);
+  if (rc != GSK_OK) return rc;
+  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(mean_out, d_mean, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(var_out, d_var, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+  if (d_nn)
+    GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(nneigh_out, d_nn, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+  if (d_idx)
+    GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(neigh_idx_out, d_idx, sizeof(int) * (size_t)count * k, cudaMemcpyDeviceToHost, ctx->stream));
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  return GSK_OK;
+}
+
+extern "C" int gsk_measure_fp64_peak(gsk_ctx *ctx, double *dfma_tflops, double *dmma_tflops) {
+  if (!ctx || !dfma_tflops || !dmma_tflops) return GSK_ERR_INVALID;
+  GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  return gsk_peak_measure(ctx, dfma_tflops, dmma_tflops);
+}

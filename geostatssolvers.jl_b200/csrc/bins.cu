@@ -1,0 +1,206 @@
+// bins.cu — K1: uniform-grid spatial bins over the samples (count → scan → scatter), replacing the
+// KD-tree the reference builds inside KNearestSearch/KBallSearch (ref: src/ui.jl:27,30, called from
+// src/estimation/krig.jl:117). Samples are re-ordered by cell into 32-byte records so that a row of
+// cells is one contiguous, 16-byte-aligned range — the unit the search kernel bulk-copies (TMA) into
+// shared memory.
+#include <math.h>
+
+#include <algorithm>
+
+#include "gsk_internal.cuh"
+
+namespace {
+
+__device__ __forceinline__ int bin_of(double x, double lo, double inv, int nb) {
+  double f = floor((x - lo) * inv);
+  int b = (f < 0.0) ? 0 : ((f >= (double)nb) ? nb - 1 : (int)f);
+  return b;
+}
+
+__global__ void pack_and_count_kernel(const double *__restrict__ x, const double *__restrict__ y,
+                                      const double *__restrict__ z, const double *__restrict__ v, long long n,
+                                      GskBins bins, double4 *__restrict__ rec_orig, int *__restrict__ cell_of,
+                                      int *__restrict__ counts) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double px = x[i], py = y ? y[i] : 0.0, pz = z ? z[i] : 0.0;
+  rec_orig[i] = make_double4(px, py, pz, v[i]);
+  int bx = bin_of(px, bins.lo[0], bins.inv[0], bins.nb[0]);
+  int by = bin_of(py, bins.lo[1], bins.inv[1], bins.nb[1]);
+  int bz = bin_of(pz, bins.lo[2], bins.inv[2], bins.nb[2]);
+  int c = (bz * bins.nb[1] + by) * bins.nb[0] + bx;
+  cell_of[i] = c;
+  atomicAdd(&counts[c], 1);
+}
+
+// exclusive scan of `counts` (ncells entries) into cell_start (ncells+1); one CTA, chunked
+__global__ void scan_kernel(const int *__restrict__ counts, long long ncells, int *__restrict__ cell_start) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (long long base = 0; base < ncells; base += blockDim.x) {
+    long long i = base + tid;
+    int v = (i < ncells) ? counts[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int w = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      warp_sums[lane] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    int excl = carry + warp_sums[wid] + incl - v;
+    if (i < ncells) cell_start[i] = excl;
+    __syncthreads();
+    if (tid == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (tid == 0) cell_start[ncells] = carry;
+}
+
+__global__ void scatter_kernel(const double4 *__restrict__ rec_orig, const int *__restrict__ cell_of, long long n,
+                               const int *__restrict__ cell_start, int *__restrict__ cursor,
+                               double4 *__restrict__ rec_sorted) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = cell_of[i];
+  int slot = cell_start[c] + atomicAdd(&cursor[c], 1);
+  double4 r = rec_orig[i];
+  r.w = __longlong_as_double((long long)i);
+  rec_sorted[slot] = r;
+}
+
+// make the within-cell order deterministic (ascending original index): insertion sort per cell
+__global__ void cell_sort_kernel(double4 *__restrict__ rec_sorted, const int *__restrict__ cell_start,
+                                 long long ncells) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncells) return;
+  int s = cell_start[c], e = cell_start[c + 1];
+  for (int i = s + 1; i < e; ++i) {
+    double4 key = rec_sorted[i];
+    long long ki = __double_as_longlong(key.w);
+    int j = i - 1;
+    while (j >= s && __double_as_longlong(rec_sorted[j].w) > ki) {
+      rec_sorted[j + 1] = rec_sorted[j];
+      --j;
+    }
+    rec_sorted[j + 1] = key;
+  }
+}
+
+}  // namespace
+
+int gsk_build_bins(gsk_ctx *ctx, const double *hx, const double *hy, const double *hz, const double *hv, long long n,
+                   int dim, int k) {
+  // ---- bounding box and bin lattice (host, O(n)) ----
+  const double *h[3] = {hx, hy, hz};
+  double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  for (int d = 0; d < dim; ++d) {
+    double mn = h[d][0], mx = h[d][0];
+    for (long long i = 1; i < n; ++i) {
+      mn = std::min(mn, h[d][i]);
+      mx = std::max(mx, h[d][i]);
+    }
+    if (!(mn == mn) || !(mx == mx) || isinf(mn) || isinf(mx)) {
+      ctx->err = "sample coordinates must be finite";
+      return GSK_ERR_INVALID;
+    }
+    lo[d] = mn;
+    hi[d] = mx;
+  }
+  // cells sized for ~occ samples each (k/4…k/2 per cell, capped)
+  double occ = std::min(8.0, std::max(2.0, k / 6.0));
+  int live = 0;
+  double vol = 1.0;
+  for (int d = 0; d < dim; ++d)
+    if (hi[d] > lo[d]) { vol *= (hi[d] - lo[d]); ++live; }
+  GskBins b{};
+  double side = (live > 0) ? pow(vol * occ / (double)n, 1.0 / live) : 1.0;
+  long long ncells = 1;
+  for (int d = 0; d < 3; ++d) {
+    double ext = (d < dim) ? hi[d] - lo[d] : 0.0;
+    int nb = 1;
+    if (ext > 0.0 && side > 0.0) nb = (int)std::min(4096.0, std::max(1.0, floor(ext / side)));
+    b.nb[d] = nb;
+    b.lo[d] = (d < dim) ? lo[d] : 0.0;
+    b.cell[d] = (ext > 0.0) ? ext / nb : 1.0;
+    b.inv[d] = 1.0 / b.cell[d];
+    ncells *= nb;
+  }
+  while (ncells > (1ll << 24)) {  // cap the table at 16M cells
+    int dmax = 0;
+    for (int d = 1; d < 3; ++d) if (b.nb[d] > b.nb[dmax]) dmax = d;
+    ncells /= b.nb[dmax];
+    b.nb[dmax] = (b.nb[dmax] + 1) / 2;
+    ncells *= b.nb[dmax];
+    b.cell[dmax] = (hi[dmax] - lo[dmax]) / b.nb[dmax];
+    b.inv[dmax] = 1.0 / b.cell[dmax];
+  }
+  b.ncells = ncells;
+  b.cell_max = 0.0;
+  for (int d = 0; d < dim; ++d) b.cell_max = std::max(b.cell_max, b.cell[d]);
+
+  // initial search margin: radius of the ball holding k samples at the mean density
+  {
+    double dens = (live > 0 && vol > 0) ? (double)n / vol : 1.0;
+    double cd = (live <= 1) ? 2.0 : (live == 2 ? M_PI : 4.0 * M_PI / 3.0);
+    double r0 = (live > 0) ? pow((double)k / (dens * cd), 1.0 / live) : 0.0;
+    for (int d = 0; d < 3; ++d) {
+      int m = (d < dim && hi[d] > lo[d]) ? (int)ceil(1.15 * r0 / b.cell[d]) : 0;
+      ctx->margin0[d] = std::max(m, (d < dim) ? 1 : 0);
+    }
+  }
+
+  // ---- device buffers ----
+  cudaStream_t st = ctx->stream;
+  double *tmp = nullptr;
+  int *cell_of = nullptr, *counts = nullptr;
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&tmp, sizeof(double) * 4 * (size_t)n));
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&cell_of, sizeof(int) * (size_t)n));
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&counts, sizeof(int) * (size_t)ncells * 2));
+  int *cursor = counts + ncells;
+  cudaFree(ctx->d_rec_orig);
+  cudaFree(ctx->d_rec_sorted);
+  cudaFree(ctx->d_cell_start);
+  ctx->d_rec_orig = ctx->d_rec_sorted = nullptr;
+  ctx->d_cell_start = nullptr;
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_rec_orig, sizeof(double4) * (size_t)n));
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_rec_sorted, sizeof(double4) * (size_t)(n + 1)));
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_cell_start, sizeof(int) * (size_t)(ncells + 1)));
+  double *dx = tmp, *dy = tmp + n, *dz = tmp + 2 * n, *dv = tmp + 3 * n;
+  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(dx, hx, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  if (dim > 1) GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(dy, hy, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  if (dim > 2) GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(dz, hz, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(dv, hv, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  GSK_CUDA_CHECK(ctx, cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)ncells * 2, st));
+
+  b.rec = ctx->d_rec_sorted;
+  b.cell_start = ctx->d_cell_start;
+  const int TB = 256;
+  unsigned gn = (unsigned)((n + TB - 1) / TB);
+  pack_and_count_kernel<<<gn, TB, 0, st>>>(dx, dim > 1 ? dy : nullptr, dim > 2 ? dz : nullptr, dv, n, b,
+                                          ctx->d_rec_orig, cell_of, counts);
+  scan_kernel<<<1, 1024, 0, st>>>(counts, ncells, ctx->d_cell_start);
+  scatter_kernel<<<gn, TB, 0, st>>>(ctx->d_rec_orig, cell_of, n, ctx->d_cell_start, cursor, ctx->d_rec_sorted);
+  cell_sort_kernel<<<(unsigned)((ncells + TB - 1) / TB), TB, 0, st>>>(ctx->d_rec_sorted, ctx->d_cell_start, ncells);
+  GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  cudaFree(tmp);
+  cudaFree(cell_of);
+  cudaFree(counts);
+  ctx->bins = b;
+  return GSK_OK;
+}

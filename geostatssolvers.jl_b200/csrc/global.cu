@@ -1,0 +1,538 @@
+// global.cu — K4 + K5: the global ("exact") kriging system, replacing exactsolve's
+// `fit(estimator, pdata)` once (ref: src/estimation/krig.jl:176) and `predictprob(krig, var, pdomain[ind])`
+// for every target (krig.jl:180).
+//
+// Plan (once per GPU):  C = sill − Γ (n×n, FP64) is assembled on the device, factorised C = L Lᵀ by a
+// blocked right-looking Cholesky, and L is inverted block row by block row (Linv). With
+// E = [z (−μ) | f_1 … f_c] (drift columns: OK → ones, UK → monomials), Y_E = Linv·E and the constant
+// Gram block G_EE = Y_EᵀY_E are kept resident.
+// Execute (per batch of targets): the block-support right-hand sides B (n × batch) are assembled,
+// then ONE triangular GEMM  Y = Linv·B  runs with a fused epilogue that never writes Y: per target it
+// reduces ‖y‖² and Y_Eᵀy, i.e. the Gram entries Gm[b,b], Gm[E,b] of the same block elimination the
+// local kernel uses (local_solve.cuh), from which ν, mean and variance follow:
+//   ν = Gff⁻¹(Gfb − f₀),  mean = Gbz − Gfz·ν,  var = sill − (Gbb − Gfb·ν + f₀·ν)      (SK: μ + Gbz, sill − Gbb)
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "gsk_internal.cuh"
+
+namespace {
+
+constexpr int NB = 64;   // block size of the factorisation and of the GEMM tiles
+constexpr int BK = 16;
+
+struct GArgs {
+  const double4 *rec;  // samples {x,y,z,value}
+  long long n, np;     // samples, padded to a multiple of NB
+  GskVario vg;
+  int dim;
+};
+
+// ---- C assembly (lower triangle + diagonal; padded rows/cols = identity) ----
+template <int VK>
+__global__ void assemble_kernel(GArgs g, double *__restrict__ A) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long j = blockIdx.y;
+  if (i >= g.np || i < j) return;
+  double v;
+  if (i >= g.n || j >= g.n) v = (i == j) ? 1.0 : 0.0;
+  else if (i == j) v = g.vg.sill;
+  else {
+    double4 a = g.rec[i], b = g.rec[j];
+    double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+    double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    v = gsk_cov<VK>(g.vg, d2);
+  }
+  A[i + j * g.np] = v;
+}
+
+// ---- 64×64 tile product on the FP64 pipe: acc(4×4 per thread) += A(64×K)·B(K×64) ----
+// A column-major (lda). B either column-major K×64 (TRANSB=false, element (k,n) at B[k + n·ldb])
+// or given as 64×K column-major to be used transposed (TRANSB=true, element (k,n) at B[n + k·ldb]).
+template <bool TRANSB>
+__device__ __forceinline__ void tile_mma(const double *__restrict__ A, long long lda, const double *__restrict__ B,
+                                         long long ldb, int K, double (&acc)[4][4], double (*As)[NB + 1],
+                                         double (*Bs)[NB + 1]) {
+  const int tid = threadIdx.x;
+  const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    // A tile: 64 rows × 16 k
+    for (int e = tid; e < NB * BK; e += 256) {
+      int m = e & 63, k = e >> 6;
+      As[k][m] = A[m + (long long)(k0 + k) * lda];
+    }
+    if (TRANSB) {
+      for (int e = tid; e < NB * BK; e += 256) {
+        int nn = e & 63, k = e >> 6;
+        Bs[k][nn] = B[nn + (long long)(k0 + k) * ldb];
+      }
+    } else {
+      for (int e = tid; e < NB * BK; e += 256) {
+        int k = e & 15, nn = e >> 4;
+        Bs[k][nn] = B[(k0 + k) + (long long)nn * ldb];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[k][tm + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tn + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- diagonal block: Cholesky of A[j0:j0+64, j0:j0+64] in place, and its inverse into Dinv ----
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double *__restrict__ A, long long ld, long long j0,
+                                                         double *__restrict__ Dinv) {
+  __shared__ double L[NB][NB + 1];
+  const int tid = threadIdx.x;
+  double *blk = A + j0 + j0 * ld;
+  for (int e = tid; e < NB * NB; e += 256) {
+    int i = e & 63, j = e >> 6;
+    L[i][j] = (i >= j) ? blk[i + (long long)j * ld] : 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < NB; ++j) {
+    if (tid == 0) L[j][j] = sqrt(L[j][j]);
+    __syncthreads();
+    const double d = L[j][j];
+    if (tid > j && tid < NB) L[tid][j] /= d;
+    __syncthreads();
+    // trailing update of the lower triangle
+    for (int e = tid; e < (NB - j - 1) * (NB - j - 1); e += 256) {
+      int i = j + 1 + e % (NB - j - 1), c = j + 1 + e / (NB - j - 1);
+      if (i >= c) L[i][c] -= L[i][j] * L[c][j];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < NB * NB; e += 256) {
+    int i = e & 63, j = e >> 6;
+    if (i >= j) blk[i + (long long)j * ld] = L[i][j];
+  }
+  // inverse of the lower-triangular block: thread c solves L x = e_c (column c of the inverse)
+  if (tid < NB) {
+    const int c = tid;
+    double *x = Dinv + c * NB;
+    for (int i = 0; i < NB; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int p = c; p < i; ++p) s -= L[i][p] * x[p];
+      x[i] = (i >= c) ? s / L[i][i] : 0.0;
+    }
+  }
+}
+
+// ---- panel below the diagonal block: P = A[i-block, j-block] · Dinvᵀ, in place ----
+__global__ void __launch_bounds__(256) trsm_panel_kernel(double *__restrict__ A, long long ld, long long j0,
+                                                         const double *__restrict__ Dinv) {
+  __shared__ double As[BK][NB + 1];
+  __shared__ double Bs[BK][NB + 1];
+  const long long i0 = j0 + NB + (long long)blockIdx.x * NB;
+  double *blk = A + i0 + j0 * ld;
+  double acc[4][4] = {};
+  // the whole 64×64 source tile is consumed before anything is written back (same CTA owns it)
+  tile_mma<true>(blk, ld, Dinv, NB, NB, acc, As, Bs);
+  const int tm = (threadIdx.x & 15) * 4, tn = (threadIdx.x >> 4) * 4;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) blk[(tm + i) + (long long)(tn + j) * ld] = acc[i][j];
+}
+
+// ---- trailing update: A[bi, bj] −= P[bi]·P[bj]ᵀ for all tile pairs bi >= bj below the panel ----
+__global__ void __launch_bounds__(256) syrk_kernel(double *__restrict__ A, long long ld, long long j0, int nrem) {
+  __shared__ double As[BK][NB + 1];
+  __shared__ double Bs[BK][NB + 1];
+  // linear index over the lower-triangular tile pairs
+  int t = blockIdx.x;
+  int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  while (bi * (bi + 1) / 2 > t) --bi;
+  int bj = t - bi * (bi + 1) / 2;
+  if (bi >= nrem) return;
+  const long long r0 = j0 + NB + (long long)bi * NB, c0 = j0 + NB + (long long)bj * NB;
+  double acc[4][4] = {};
+  tile_mma<true>(A + r0 + j0 * ld, ld, A + c0 + j0 * ld, ld, NB, acc, As, Bs);
+  const int tm = (threadIdx.x & 15) * 4, tn = (threadIdx.x >> 4) * 4;
+  double *blk = A + r0 + c0 * ld;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) blk[(tm + i) + (long long)(tn + j) * ld] -= acc[i][j];
+}
+
+// ---- Linv block row i:  X[i, jb] = −Dinv_i · Σ_{m=jb}^{i−1} L[i, m]·X[m, jb]  (jb < i);  X[i,i] = Dinv_i ----
+__global__ void __launch_bounds__(256) linv_row_kernel(const double *__restrict__ A, double *__restrict__ X,
+                                                       long long ld, int bi, const double *__restrict__ Dinv_all) {
+  // As/Bs are only live inside tile_mma; T reuses the same shared memory afterwards
+  __shared__ double buf[NB * (NB + 1)];
+  double (*As)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(buf);
+  double (*Bs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(buf + BK * (NB + 1));
+  double (*T)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(buf);
+  const int jb = blockIdx.x;
+  const long long i0 = (long long)bi * NB, j0 = (long long)jb * NB;
+  const double *Di = Dinv_all + (size_t)bi * NB * NB;
+  const int tm = (threadIdx.x & 15) * 4, tn = (threadIdx.x >> 4) * 4;
+  double *out = X + i0 + j0 * ld;
+  if (jb == bi) {
+    for (int e = threadIdx.x; e < NB * NB; e += 256) {
+      int i = e & 63, j = e >> 6;
+      out[i + (long long)j * ld] = Di[i + j * NB];
+    }
+    return;
+  }
+  double acc[4][4] = {};
+  tile_mma<false>(A + i0 + j0 * ld, ld, X + j0 + j0 * ld, ld, (bi - jb) * NB, acc, As, Bs);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) T[tm + i][tn + j] = acc[i][j];
+  __syncthreads();
+  // out = −Di · T   (Di lower triangular 64×64)
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = tm + i, c = tn + j;
+      double s = 0.0;
+      for (int p = 0; p <= r; ++p) s = fma(Di[r + p * NB], T[p][c], s);
+      out[r + (long long)c * ld] = -s;
+    }
+}
+
+// ---- Y_E = Linv · E  (n × ne, tall-skinny): one warp per row ----
+__global__ void linv_times_e_kernel(const double *__restrict__ X, long long ld, long long np,
+                                    const double *__restrict__ E, int ne, double *__restrict__ YE) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= np) return;
+  for (int c = 0; c < ne; ++c) {
+    double s = 0.0;
+    for (long long p = lane; p <= row; p += 32) s = fma(X[row + p * ld], E[p + c * np], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) YE[row + c * np] = s;
+  }
+}
+
+// G_EE = Y_EᵀY_E, one CTA, deterministic
+__global__ void gram_ee_kernel(const double *__restrict__ YE, long long np, int ne, double *__restrict__ GEE) {
+  __shared__ double red[256];
+  for (int a = 0; a < ne; ++a)
+    for (int b = 0; b < ne; ++b) {
+      double s = 0.0;
+      for (long long i = threadIdx.x; i < np; i += 256) s = fma(YE[i + a * np], YE[i + b * np], s);
+      red[threadIdx.x] = s;
+      __syncthreads();
+      for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) GEE[a * ne + b] = red[0];
+      __syncthreads();
+    }
+}
+
+// E columns: z (− μ), then drift monomials of the samples; padded rows 0
+__global__ void build_e_kernel(GArgs g, GskEstimator es, double *__restrict__ E) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.np) return;
+  const int ne = 1 + es.nterms;
+  if (i >= g.n) {
+    for (int c = 0; c < ne; ++c) E[i + c * g.np] = 0.0;
+    return;
+  }
+  double4 r = g.rec[i];
+  E[i] = (es.kind == GSK_EST_SIMPLE) ? r.w - es.sk_mean : r.w;
+  for (int t = 0; t < es.nterms; ++t) {
+    double v = 1.0;
+    if (es.kind == GSK_EST_UNIVERSAL)
+      v = gsk_ipow(r.x, es.exps[t][0]) * gsk_ipow(r.y, es.exps[t][1]) * gsk_ipow(r.z, es.exps[t][2]);
+    E[i + (1 + t) * g.np] = v;
+  }
+}
+
+// ---- execute: right-hand sides of a batch, B[i + t·np] = mean_q C(‖c_t + δ_q − x_i‖) ----
+template <int VK>
+__global__ void rhs_kernel(GArgs g, GskTargets tg, const double *__restrict__ sup, int nsup, long long first,
+                           int nbatch, double *__restrict__ Bm) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int t = blockIdx.y;
+  if (i >= g.np || t >= nbatch) return;
+  double v = 0.0;
+  if (i < g.n) {
+    long long lin = first + t;
+    double tc[3] = {0.0, 0.0, 0.0};
+    if (tg.is_grid) {
+      long long rem = lin;
+      for (int d = 0; d < tg.dim; ++d) {
+        long long c = rem % tg.gdim[d];
+        rem /= tg.gdim[d];
+        tc[d] = gsk_cell_center(tg.gorg[d], tg.gsp[d], c);
+      }
+    } else {
+      for (int d = 0; d < tg.dim; ++d) tc[d] = tg.pts[d][lin];
+    }
+    double4 r = g.rec[i];
+    double acc = 0.0;
+    for (int q = 0; q < nsup; ++q) {
+      double dx = (tc[0] + sup[q]) - r.x, dy = (tc[1] + sup[nsup + q]) - r.y, dz = (tc[2] + sup[2 * nsup + q]) - r.z;
+      double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+      acc += gsk_cov<VK>(g.vg, d2);
+    }
+    v = acc / (double)nsup;
+  }
+  Bm[i + (long long)t * g.np] = v;
+}
+
+// ---- the hot kernel: Y tile = Linv[mt, 0..mt]·B[0..mt, nt]; epilogue reduces Y² and Y·Y_E per target ----
+// partial[(mt·(1+ne) + s)·nbpad + t]
+__global__ void __launch_bounds__(256) ygemm_kernel(const double *__restrict__ X, long long ld,
+                                                    const double *__restrict__ Bm, const double *__restrict__ YE,
+                                                    int ne, long long nbpad, double *__restrict__ partial) {
+  __shared__ double As[BK][NB + 1];
+  __shared__ double Bs[BK][NB + 1];
+  __shared__ double red[16][NB + 1];
+  const int nt = blockIdx.x, mt = gridDim.y - 1 - blockIdx.y;  // longest row tiles first
+  const long long i0 = (long long)mt * NB, t0 = (long long)nt * NB;
+  double acc[4][4] = {};
+  tile_mma<false>(X + i0, ld, Bm + t0 * ld, ld, (mt + 1) * NB, acc, As, Bs);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int tm = tx * 4, tn = ty * 4;
+  for (int s = 0; s <= ne; ++s) {
+    double w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = (s == 0) ? 0.0 : YE[i0 + tm + i + (long long)(s - 1) * ld];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double v = 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v = fma(acc[i][j], (s == 0) ? acc[i][j] : w[i], v);
+      red[tx][tn + j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NB) {
+      double v = 0.0;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v += red[r][threadIdx.x];
+      partial[((long long)mt * (1 + ne) + s) * nbpad + t0 + threadIdx.x] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- per-target epilogue: reduce the partials over the row tiles, then the e×e algebra ----
+__global__ void global_epilogue_kernel(const double *__restrict__ partial, int nmt, int ne, long long nbpad,
+                                       int nbatch, const double *__restrict__ GEE, GskEstimator es, GskTargets tg,
+                                       double sill, unsigned flags, long long first, double *__restrict__ mean,
+                                       double *__restrict__ var) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nbatch) return;
+  double g[2 + GSK_MAX_DRIFT_TERMS];
+  for (int s = 0; s <= ne; ++s) {
+    double v = 0.0;
+    for (int mt = 0; mt < nmt; ++mt) v += partial[((long long)mt * (1 + ne) + s) * nbpad + t];
+    g[s] = v;
+  }
+  const double gbb = g[0], gbz = g[1];
+  const int c = es.nterms;
+  double mu, s2;
+  if (c == 0) {
+    mu = es.sk_mean + gbz;
+    s2 = sill - gbb;
+  } else {
+    double f0[GSK_MAX_DRIFT_TERMS], nu[GSK_MAX_DRIFT_TERMS], Lf[GSK_MAX_DRIFT_TERMS][GSK_MAX_DRIFT_TERMS];
+    double tc[3] = {0.0, 0.0, 0.0};
+    long long lin = first + t;
+    if (tg.is_grid) {
+      long long rem = lin;
+      for (int d = 0; d < tg.dim; ++d) {
+        long long cc = rem % tg.gdim[d];
+        rem /= tg.gdim[d];
+        tc[d] = gsk_cell_center(tg.gorg[d], tg.gsp[d], cc);
+      }
+    } else {
+      for (int d = 0; d < tg.dim; ++d) tc[d] = tg.pts[d][lin];
+    }
+    for (int j = 0; j < c; ++j)
+      f0[j] = (es.kind == GSK_EST_ORDINARY)
+                  ? 1.0
+                  : gsk_ipow(tc[0], es.exps[j][0]) * gsk_ipow(tc[1], es.exps[j][1]) * gsk_ipow(tc[2], es.exps[j][2]);
+    // Gff = GEE[1+a][1+b], Gfz = GEE[1+a][0]
+    for (int j = 0; j < c; ++j) {
+      double d = GEE[(1 + j) * ne + 1 + j];
+      for (int p = 0; p < j; ++p) d -= Lf[j][p] * Lf[j][p];
+      d = sqrt(d);
+      Lf[j][j] = d;
+      for (int i = j + 1; i < c; ++i) {
+        double s = GEE[(1 + i) * ne + 1 + j];
+        for (int p = 0; p < j; ++p) s -= Lf[i][p] * Lf[j][p];
+        Lf[i][j] = s / d;
+      }
+    }
+    for (int j = 0; j < c; ++j) {
+      double s = g[2 + j] - f0[j];
+      for (int p = 0; p < j; ++p) s -= Lf[j][p] * nu[p];
+      nu[j] = s / Lf[j][j];
+    }
+    for (int j = c - 1; j >= 0; --j) {
+      double s = nu[j];
+      for (int p = j + 1; p < c; ++p) s -= Lf[p][j] * nu[p];
+      nu[j] = s / Lf[j][j];
+    }
+    double mz = 0.0, mb = 0.0, mf = 0.0;
+    for (int j = 0; j < c; ++j) {
+      mz += GEE[(1 + j) * ne + 0] * nu[j];
+      mb += g[2 + j] * nu[j];
+      mf += f0[j] * nu[j];
+    }
+    mu = gbz - mz;
+    s2 = sill - (gbb - mb + mf);
+  }
+  if (flags & GSK_FLAG_CLAMP_VARIANCE) s2 = (s2 > 0.0 || s2 != s2) ? s2 : 0.0;
+  if (flags & GSK_FLAG_SQRT_ROUNDTRIP) { double sd = sqrt(s2); s2 = sd * sd; }
+  mean[t] = mu;
+  var[t] = s2;
+}
+
+__global__ void fill_int_kernel(int *p, long long n, int v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+struct GlobalPlan {
+  long long n = 0, np = 0;
+  int ne = 0;
+  double *A = nullptr;     // L (lower) after factorisation
+  double *X = nullptr;     // Linv
+  double *Dinv = nullptr;  // inverses of the diagonal blocks
+  double *E = nullptr, *YE = nullptr, *GEE = nullptr;
+  double *Bm = nullptr, *partial = nullptr;
+  long long batch = 0;
+};
+
+void gsk_global_free(gsk_ctx *ctx) {
+  GlobalPlan *g = ctx->gplan;
+  if (!g) return;
+  cudaFree(g->A); cudaFree(g->X); cudaFree(g->Dinv); cudaFree(g->E); cudaFree(g->YE); cudaFree(g->GEE);
+  cudaFree(g->Bm); cudaFree(g->partial);
+  delete g;
+  ctx->gplan = nullptr;
+}
+
+int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const double *hz, const double *hv) {
+  const long long n = ctx->prob.n_samples;
+  const int dim = ctx->prob.dim;
+  cudaStream_t st = ctx->stream;
+  GlobalPlan *g = new GlobalPlan();
+  ctx->gplan = g;
+  g->n = n;
+  g->np = (n + NB - 1) / NB * NB;
+  g->ne = 1 + ctx->es.nterms;
+  const long long np = g->np;
+  const int nblk = (int)(np / NB);
+
+  // samples → {x,y,z,value} records
+  std::vector<double4> rec((size_t)n);
+  for (long long i = 0; i < n; ++i)
+    rec[(size_t)i] = make_double4(hx[i], dim > 1 ? hy[i] : 0.0, dim > 2 ? hz[i] : 0.0, hv[i]);
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_rec_orig, sizeof(double4) * (size_t)n));
+  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_rec_orig, rec.data(), sizeof(double4) * (size_t)n, cudaMemcpyHostToDevice, st));
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->A, sizeof(double) * (size_t)np * np));
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->X, sizeof(double) * (size_t)np * np));
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->Dinv, sizeof(double) * (size_t)nblk * NB * NB));
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->E, sizeof(double) * (size_t)np * g->ne));
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->YE, sizeof(double) * (size_t)np * g->ne));
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->GEE, sizeof(double) * (size_t)g->ne * g->ne));
+  GSK_CUDA_CHECK(ctx, cudaMemsetAsync(g->X, 0, sizeof(double) * (size_t)np * np, st));
+
+  GArgs ga{ctx->d_rec_orig, n, np, ctx->vg, dim};
+  {
+    dim3 grid((unsigned)((np + 255) / 256), (unsigned)np);
+    switch (ctx->vg.kind) {
+      case GSK_VARIO_GAUSSIAN: assemble_kernel<GSK_VARIO_GAUSSIAN><<<grid, 256, 0, st>>>(ga, g->A); break;
+      case GSK_VARIO_SPHERICAL: assemble_kernel<GSK_VARIO_SPHERICAL><<<grid, 256, 0, st>>>(ga, g->A); break;
+      default: assemble_kernel<GSK_VARIO_EXPONENTIAL><<<grid, 256, 0, st>>>(ga, g->A); break;
+    }
+  }
+  // blocked right-looking Cholesky
+  for (int jb = 0; jb < nblk; ++jb) {
+    const long long j0 = (long long)jb * NB;
+    potrf_diag_kernel<<<1, 256, 0, st>>>(g->A, np, j0, g->Dinv + (size_t)jb * NB * NB);
+    const int nrem = nblk - jb - 1;
+    if (nrem > 0) {
+      trsm_panel_kernel<<<nrem, 256, 0, st>>>(g->A, np, j0, g->Dinv + (size_t)jb * NB * NB);
+      syrk_kernel<<<(unsigned)((long long)nrem * (nrem + 1) / 2), 256, 0, st>>>(g->A, np, j0, nrem);
+    }
+  }
+  // Linv, block row by block row
+  for (int bi = 0; bi < nblk; ++bi) linv_row_kernel<<<bi + 1, 256, 0, st>>>(g->A, g->X, np, bi, g->Dinv);
+  // E, Y_E, G_EE
+  build_e_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(ga, ctx->es, g->E);
+  linv_times_e_kernel<<<(unsigned)((np + 7) / 8), 256, 0, st>>>(g->X, np, np, g->E, g->ne, g->YE);
+  gram_ee_kernel<<<1, 256, 0, st>>>(g->YE, np, g->ne, g->GEE);
+  GSK_CUDA_CHECK(ctx, cudaGetLastError());
+
+  // batch of targets per GEMM: bound B to ~2 GB
+  long long batch = (long long)((2.0e9 / 8.0) / (double)np);
+  batch = std::max<long long>(NB, std::min<long long>(batch, 32768) / NB * NB);
+  g->batch = batch;
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->Bm, sizeof(double) * (size_t)np * batch));
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->partial, sizeof(double) * (size_t)nblk * (1 + g->ne) * batch));
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  return GSK_OK;
+}
+
+int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, double *d_mean, double *d_var, int *d_nn,
+                       int *launches) {
+  GlobalPlan *g = ctx->gplan;
+  if (!g) { ctx->err = "global plan missing"; return GSK_ERR_STATE; }
+  cudaStream_t st = ctx->stream;
+  const long long np = g->np;
+  const int nblk = (int)(np / NB);
+  GArgs ga{ctx->d_rec_orig, g->n, np, ctx->vg, ctx->prob.dim};
+  for (long long off = 0; off < count; off += g->batch) {
+    const int nb = (int)std::min<long long>(g->batch, count - off);
+    const int nbp = (nb + NB - 1) / NB * NB;
+    if (nbp > nb)  // zero the padded target columns so the GEMM reads defined data
+      GSK_CUDA_CHECK(ctx, cudaMemsetAsync(g->Bm + (size_t)nb * np, 0, sizeof(double) * (size_t)(nbp - nb) * np, st));
+    dim3 grid((unsigned)((np + 255) / 256), (unsigned)nb);
+    switch (ctx->vg.kind) {
+      case GSK_VARIO_GAUSSIAN:
+        rhs_kernel<GSK_VARIO_GAUSSIAN><<<grid, 256, 0, st>>>(ga, ctx->tg, ctx->d_sup, ctx->prob.n_support, first + off, nb, g->Bm);
+        break;
+      case GSK_VARIO_SPHERICAL:
+        rhs_kernel<GSK_VARIO_SPHERICAL><<<grid, 256, 0, st>>>(ga, ctx->tg, ctx->d_sup, ctx->prob.n_support, first + off, nb, g->Bm);
+        break;
+      default:
+        rhs_kernel<GSK_VARIO_EXPONENTIAL><<<grid, 256, 0, st>>>(ga, ctx->tg, ctx->d_sup, ctx->prob.n_support, first + off, nb, g->Bm);
+        break;
+    }
+    ygemm_kernel<<<dim3((unsigned)(nbp / NB), (unsigned)nblk), 256, 0, st>>>(g->X, np, g->Bm, g->YE, g->ne, g->batch,
+                                                                            g->partial);
+    global_epilogue_kernel<<<(nb + 127) / 128, 128, 0, st>>>(g->partial, nblk, g->ne, g->batch, nb, g->GEE, ctx->es,
+                                                             ctx->tg, ctx->vg.sill, ctx->prob.flags, first + off,
+                                                             d_mean + off, d_var + off);
+    if (launches) *launches += 3;
+  }
+  if (d_nn) {
+    fill_int_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(d_nn, count, (int)g->n);
+    if (launches) *launches += 1;
+  }
+  GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  return GSK_OK;
+}

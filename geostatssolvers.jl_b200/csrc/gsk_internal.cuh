@@ -1,0 +1,188 @@
+// gsk_internal.cuh — shared declarations of libgskrige.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/gskrige.h"
+
+#define GSK_CUDA_CHECK(ctx, expr)                                                        \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                   \
+      return GSK_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// device-side problem description (passed by value to kernels)
+// ---------------------------------------------------------------------------------------
+struct GskVario {
+  int kind;
+  double sill;    // s
+  double cs;      // s − n'   (n' = nugget [+ Gaussian epsilon])
+  double range;   // r
+  double inv_r2;  // 1/r²
+  double inv_r;   // 1/r
+};
+
+struct GskTargets {
+  int is_grid;
+  int dim;
+  long long gdim[3];
+  double gorg[3], gsp[3];
+  const double *pts[3];  // explicit target points (device), original order
+  long long npts;
+};
+
+struct GskBins {
+  double lo[3], cell[3], inv[3];
+  int nb[3];
+  long long ncells;
+  const double4 *rec;     // samples sorted by cell: {x, y, z, original index as double bits (int64)}
+  const int *cell_start;  // ncells + 1
+  double cell_max;        // largest cell side (slack scale)
+};
+
+struct GskEstimator {
+  int kind;        // GSK_EST_*
+  int nterms;      // c: Lagrange rows (SK 0, OK 1, UK C(d+deg,deg))
+  double sk_mean;
+  int exps[GSK_MAX_DRIFT_TERMS][3];
+};
+
+struct GskLocalArgs {
+  GskTargets tg;
+  GskVario vg;
+  GskEstimator es;
+  const double4 *rec_orig;  // samples in original order: {x, y, z, value}
+  const double *sup;        // support offsets [3][nsup] (device)
+  int nsup;
+  int k;                    // clamped max neighbours
+  int min_neighbors;
+  int use_ball;
+  double radius;
+  unsigned flags;
+  long long first, count;   // slab
+  const int *nn;            // neighbours per target (slab-local)
+  const int *nbr;           // count × k original indices, −1 padded
+  double *mean, *var;       // slab-local outputs
+};
+
+struct GskSearchArgs {
+  GskTargets tg;
+  GskBins bins;
+  int k;
+  int use_ball;
+  double radius;
+  long long first, count;
+  // tile lattice (grid targets): tiles start at cell t0[d], ntile[d] tiles per axis
+  long long t0[3];
+  int ntile[3];
+  int margin0[3];  // initial block margin in bins
+  int *nn;         // out: neighbours per target
+  int *nbr;        // out: count × k original indices sorted by (d², idx), −1 padded
+};
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+struct GlobalPlan;  // global.cu
+
+struct gsk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  int sm_count = 148;
+
+  // planned problem (host copy of scalars)
+  bool planned = false;
+  gsk_problem prob{};
+  long long n_targets = 0;
+  int nterms = 0;
+
+  // resident device buffers
+  double4 *d_rec_orig = nullptr;  // n
+  double4 *d_rec_sorted = nullptr;
+  int *d_cell_start = nullptr;
+  double *d_sup = nullptr;
+  double *d_pts[3] = {nullptr, nullptr, nullptr};
+  GskBins bins{};
+  GskTargets tg{};
+  GskVario vg{};
+  GskEstimator es{};
+  int margin0[3] = {1, 1, 1};
+
+  // scratch that grows on demand
+  int *d_nn = nullptr;
+  int *d_nbr = nullptr;
+  size_t cap_nn = 0, cap_nbr = 0;
+  double *d_mean = nullptr, *d_var = nullptr;
+  size_t cap_out = 0;
+
+  GlobalPlan *gplan = nullptr;
+
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  gsk_timing timing{};
+  bool timing_pending = false;
+};
+
+// bins.cu
+int gsk_build_bins(gsk_ctx *ctx, const double *hx, const double *hy, const double *hz, const double *hv, long long n,
+                   int dim, int k);
+// search.cu
+int gsk_launch_search(gsk_ctx *ctx, long long first, long long count, int *d_nn, int *d_nbr, int *launches);
+// local_solve*.cu
+int gsk_launch_local_solve(gsk_ctx *ctx, long long first, long long count, const int *d_nn, const int *d_nbr,
+                           double *d_mean, double *d_var, int *launches);
+// global.cu
+int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const double *hz, const double *hv);
+int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, double *d_mean, double *d_var, int *d_nn,
+                       int *launches);
+void gsk_global_free(gsk_ctx *ctx);
+// peak.cu
+int gsk_peak_measure(gsk_ctx *ctx, double *dfma, double *dmma);
+
+// ---------------------------------------------------------------------------------------
+// device helpers shared by kernels
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+// target centroid: origin + (i + 0.5)·spacing, no FMA (bit-identical to the oracle)
+__device__ __forceinline__ double gsk_cell_center(double org, double sp, long long i) {
+  return __dadd_rn(org, __dmul_rn((double)i + 0.5, sp));
+}
+
+// covariance C(h) = sill − γ(h) from the squared distance (d2 == 0 → sill)
+template <int VK>
+__device__ __forceinline__ double gsk_cov(const GskVario &v, double d2) {
+  double c;
+  if (VK == GSK_VARIO_GAUSSIAN) {
+    c = v.cs * exp(-3.0 * d2 * v.inv_r2);
+  } else if (VK == GSK_VARIO_SPHERICAL) {
+    double u = d2 * v.inv_r2;
+    double t = sqrt(u);
+    double g = fma(t, fma(0.5, u, -1.5), 1.0);  // 1 − 1.5t + 0.5t³
+    c = (u < 1.0) ? v.cs * g : 0.0;
+  } else {
+    c = v.cs * exp(-3.0 * sqrt(d2) * v.inv_r);
+  }
+  return (d2 > 0.0) ? c : v.sill;
+}
+
+__device__ __forceinline__ double gsk_cov_rt(const GskVario &v, double d2) {
+  switch (v.kind) {
+    case GSK_VARIO_GAUSSIAN: return gsk_cov<GSK_VARIO_GAUSSIAN>(v, d2);
+    case GSK_VARIO_SPHERICAL: return gsk_cov<GSK_VARIO_SPHERICAL>(v, d2);
+    default: return gsk_cov<GSK_VARIO_EXPONENTIAL>(v, d2);
+  }
+}
+
+__device__ __forceinline__ double gsk_ipow(double x, int e) {
+  double r = 1.0;
+  for (int i = 0; i < e; ++i) r *= x;
+  return r;
+}
+#endif

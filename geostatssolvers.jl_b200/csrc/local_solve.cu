@@ -1,0 +1,40 @@
+// local_solve.cu — picks the lanes/registers configuration of K3 for (k, extra rows) and launches it.
+#include "local_solve.cuh"
+
+int gsk_launch_local_solve(gsk_ctx *ctx, long long first, long long count, const int *d_nn, const int *d_nbr,
+                           double *d_mean, double *d_var, int *launches) {
+  GskLocalArgs a{};
+  a.tg = ctx->tg;
+  a.vg = ctx->vg;
+  a.es = ctx->es;
+  a.rec_orig = ctx->d_rec_orig;
+  a.sup = ctx->d_sup;
+  a.nsup = ctx->prob.n_support;
+  a.k = ctx->prob.max_neighbors;
+  a.min_neighbors = ctx->prob.min_neighbors;
+  a.use_ball = !(ctx->prob.ball_radius != ctx->prob.ball_radius);
+  a.radius = ctx->prob.ball_radius;
+  a.flags = ctx->prob.flags;
+  a.first = first;
+  a.count = count;
+  a.nn = d_nn;
+  a.nbr = d_nbr;
+  a.mean = d_mean;
+  a.var = d_var;
+  // extra rows: b, z, then the c drift rows
+  const int e = 2 + ctx->es.nterms;
+  auto rows = [&](int W) { return (a.k + W - 1) / W * W + (e + W - 1) / W * W; };
+  cudaError_t err;
+  if (rows(4) <= 12) err = gsk_local_launch_A(a, e, ctx->stream);
+  else if (rows(4) <= 24) err = gsk_local_launch_B(a, e, ctx->stream);
+  else if (rows(8) <= 40) err = gsk_local_launch_C(a, e, ctx->stream);
+  else if (rows(8) <= 80) err = gsk_local_launch_D(a, e, ctx->stream);
+  else if (rows(8) <= 128) err = gsk_local_launch_E(a, e, ctx->stream);
+  else {
+    ctx->err = "max_neighbors too large for the local kernels";
+    return GSK_ERR_UNSUPPORTED;
+  }
+  GSK_CUDA_CHECK(ctx, err);
+  if (launches) *launches += 1;
+  return GSK_OK;
+}

@@ -1,0 +1,366 @@
+// search.cu — K2: exact k-nearest / k-ball neighbour search on the bin lattice, replacing
+// `search!(neighbors, center, searcher)` (ref: src/estimation/krig.jl:210; Meshes KNearestSearch /
+// KBallSearch over a NearestNeighbors KD-tree [3P]).
+//
+// One CTA owns a tile of spatially adjacent targets (one target per thread). The CTA grows a block
+// of bins around the tile shell by shell; each shell's samples (contiguous 32-byte records per bin
+// row) are staged into shared memory with 1-D TMA bulk copies (cp.async.bulk → SASS UBLKCP) that
+// complete on an mbarrier, and every thread scans the staged records (broadcast LDS.128) keeping
+// its own ascending top-k list in shared memory ([slot][thread] layout, conflict-free). The CTA
+// stops when every thread's k-th distance is strictly inside the scanned block (or, for ball
+// search, the block covers the ball), so the result is the exact kNN set.
+//
+// Ordering key is (d², original sample index): d² is evaluated as ((dx·dx)+(dy·dy))+(dz·dz) with
+// round-to-nearest mul/add and no FMA — the oracle's chain — so neighbour sets are bit-identical
+// and ties fall to the lower sample index (north_star).
+#include <math.h>
+
+#include <algorithm>
+
+#include "gsk_internal.cuh"
+
+namespace {
+
+constexpr int NT = 128;       // targets (threads) per CTA
+constexpr int SCAP = 1024;    // staged records per chunk (32 KB)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global → shared, completion signalled on the mbarrier (bytes % 16 == 0, 16-B aligned)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ int bin_clamp(double x, double lo, double inv, int nb) {
+  double f = floor((x - lo) * inv);
+  return (f < 0.0) ? 0 : ((f >= (double)nb) ? nb - 1 : (int)f);
+}
+
+// block-wide exclusive scan of one int per thread (NT threads); returns exclusive prefix, total in *total
+__device__ __forceinline__ int block_excl_scan(int v, int *warp_buf, int *total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_buf[wid] = incl;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < NT / 32; ++w) {
+    int s = warp_buf[w];
+    if (w < wid) base += s;
+    tot += s;
+  }
+  __syncthreads();
+  *total = tot;
+  return base + incl - v;
+}
+
+template <int TX, int TY, int TZ>
+__global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
+  static_assert(TX * TY * TZ == NT, "tile must hold NT targets");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int K = a.k;
+  double4 *stage = reinterpret_cast<double4 *>(smem_raw);                 // SCAP records
+  double *topd = reinterpret_cast<double *>(smem_raw + sizeof(double4) * SCAP);  // [K][NT]
+  int *topi = reinterpret_cast<int *>(topd + (size_t)K * NT);             // [K][NT]
+  __shared__ uint64_t bar;
+  __shared__ int warp_buf[NT / 32];
+  __shared__ int sh_bb[6];
+
+  const int tid = threadIdx.x;
+  const GskTargets &tg = a.tg;
+  const GskBins &bn = a.bins;
+  const int dim = tg.dim;
+
+  // ---- my target ----
+  double tc[3] = {0.0, 0.0, 0.0};
+  long long lin = -1;
+  bool active = false;
+  int b0[3] = {0, 0, 0}, b1[3] = {0, 0, 0};  // bins overlapped by the tile's targets
+  if (tg.is_grid) {
+    int tile = blockIdx.x;
+    int tix = tile % a.ntile[0];
+    int tiy = (tile / a.ntile[0]) % a.ntile[1];
+    int tiz = tile / (a.ntile[0] * a.ntile[1]);
+    int ix = tid % TX, iy = (tid / TX) % TY, iz = tid / (TX * TY);
+    long long c[3] = {a.t0[0] + (long long)tix * TX + ix, a.t0[1] + (long long)tiy * TY + iy,
+                      a.t0[2] + (long long)tiz * TZ + iz};
+    bool inside = c[0] < tg.gdim[0] && c[1] < tg.gdim[1] && c[2] < tg.gdim[2];
+    if (inside) {
+      lin = (c[2] * tg.gdim[1] + c[1]) * tg.gdim[0] + c[0];
+      active = lin >= a.first && lin < a.first + a.count;
+    }
+    long long cmin[3] = {a.t0[0] + (long long)tix * TX, a.t0[1] + (long long)tiy * TY, a.t0[2] + (long long)tiz * TZ};
+    const int tdim[3] = {TX, TY, TZ};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (d < dim) {
+        tc[d] = gsk_cell_center(tg.gorg[d], tg.gsp[d], c[d]);
+        long long cmax = cmin[d] + tdim[d] - 1;
+        if (cmax > tg.gdim[d] - 1) cmax = tg.gdim[d] - 1;
+        double lo = gsk_cell_center(tg.gorg[d], tg.gsp[d], cmin[d]);
+        double hi = gsk_cell_center(tg.gorg[d], tg.gsp[d], cmax);
+        if (hi < lo) { double t = lo; lo = hi; hi = t; }
+        b0[d] = bin_clamp(lo, bn.lo[d], bn.inv[d], bn.nb[d]);
+        b1[d] = bin_clamp(hi, bn.lo[d], bn.inv[d], bn.nb[d]);
+      }
+    }
+  } else {
+    long long t = (long long)blockIdx.x * NT + tid;
+    active = t < a.count;
+    lin = a.first + t;
+    int mb[3] = {0, 0, 0};
+    if (active) {
+      for (int d = 0; d < dim; ++d) {
+        tc[d] = tg.pts[d][lin];
+        mb[d] = bin_clamp(tc[d], bn.lo[d], bn.inv[d], bn.nb[d]);
+      }
+    }
+    if (tid < 6) sh_bb[tid] = (tid < 3) ? 0x7fffffff : -1;
+    __syncthreads();
+    if (active) {
+      for (int d = 0; d < 3; ++d) {
+        atomicMin(&sh_bb[d], mb[d]);
+        atomicMax(&sh_bb[3 + d], mb[d]);
+      }
+    }
+    __syncthreads();
+    for (int d = 0; d < 3; ++d) { b0[d] = sh_bb[d]; b1[d] = sh_bb[3 + d]; }
+    if (b1[0] < 0) return;  // no active target in this CTA
+  }
+  // a tile with no active target exits early (uniform for the CTA)
+  if (__syncthreads_or(active ? 1 : 0) == 0) return;
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+
+  int cnt = 0;
+  double worst = INFINITY;  // k-th best d² once the list is full
+  int worst_i = 0x7fffffff;
+  const double r2 = a.use_ball ? a.radius * a.radius : INFINITY;
+  // slack that keeps the "strictly inside the scanned block" test conservative against the
+  // rounding of the bin assignment
+  const double slack = 1e-9 * bn.cell_max;
+
+  int ob0[3] = {1, 1, 1}, ob1[3] = {0, 0, 0};  // previously scanned block (empty)
+  int mg[3] = {a.margin0[0], a.margin0[1], a.margin0[2]};
+  bool have_old = false;
+
+  for (;;) {
+    int nb0[3], nb1[3];
+    bool whole = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      nb0[d] = max(0, b0[d] - mg[d]);
+      nb1[d] = min(bn.nb[d] - 1, b1[d] + mg[d]);
+      whole = whole && nb0[d] == 0 && nb1[d] == bn.nb[d] - 1;
+    }
+    const int nyr = nb1[1] - nb0[1] + 1, nzr = nb1[2] - nb0[2] + 1;
+    const int nrows = nyr * nzr;
+
+    // ---- scan the shell new \ old, NT bin rows at a time ----
+    for (int rbase = 0; rbase < nrows; rbase += NT) {
+      int r = rbase + tid;
+      int sA = 0, lA = 0, sB = 0, lB = 0;  // two record ranges (start, length)
+      if (r < nrows) {
+        int by = nb0[1] + r % nyr, bz = nb0[2] + r / nyr;
+        long long rowbase = ((long long)bz * bn.nb[1] + by) * bn.nb[0];
+        bool in_old = have_old && by >= ob0[1] && by <= ob1[1] && bz >= ob0[2] && bz <= ob1[2];
+        if (!in_old) {
+          sA = bn.cell_start[rowbase + nb0[0]];
+          lA = bn.cell_start[rowbase + nb1[0] + 1] - sA;
+        } else {
+          if (nb0[0] < ob0[0]) {
+            sA = bn.cell_start[rowbase + nb0[0]];
+            lA = bn.cell_start[rowbase + ob0[0]] - sA;
+          }
+          if (nb1[0] > ob1[0]) {
+            sB = bn.cell_start[rowbase + ob1[0] + 1];
+            lB = bn.cell_start[rowbase + nb1[0] + 1] - sB;
+          }
+        }
+      }
+      int total;
+      int off = block_excl_scan(lA + lB, warp_buf, &total);
+      for (int lo = 0; lo < total; lo += SCAP) {
+        const int hi = min(total, lo + SCAP);
+        // TMA: every thread bulk-copies the part of its ranges that falls into [lo, hi)
+        if (tid == 0) mbar_expect_tx(&bar, (uint32_t)(hi - lo) * (uint32_t)sizeof(double4));
+        {
+          int s0 = max(off, lo), e0 = min(off + lA, hi);
+          if (e0 > s0) bulk_g2s(stage + (s0 - lo), bn.rec + sA + (s0 - off), (uint32_t)(e0 - s0) * 32u, &bar);
+          int offB = off + lA;
+          int s1 = max(offB, lo), e1 = min(offB + lB, hi);
+          if (e1 > s1) bulk_g2s(stage + (s1 - lo), bn.rec + sB + (s1 - offB), (uint32_t)(e1 - s1) * 32u, &bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+        if (active) {
+          const int ns = hi - lo;
+          for (int s = 0; s < ns; ++s) {
+            const double4 rc = stage[s];
+            double dx = tc[0] - rc.x;
+            double d2 = __dmul_rn(dx, dx);
+            double dy = tc[1] - rc.y;
+            d2 = __dadd_rn(d2, __dmul_rn(dy, dy));
+            double dz = tc[2] - rc.z;
+            d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
+            if (d2 > worst) continue;
+            const int oi = (int)__double_as_longlong(rc.w);
+            if (d2 == worst && oi > worst_i) continue;
+            int p = (cnt < K) ? cnt : K - 1;
+            while (p > 0) {
+              double dp = topd[(size_t)(p - 1) * NT + tid];
+              int ip = topi[(size_t)(p - 1) * NT + tid];
+              if (d2 < dp || (d2 == dp && oi < ip)) {
+                topd[(size_t)p * NT + tid] = dp;
+                topi[(size_t)p * NT + tid] = ip;
+                --p;
+              } else {
+                break;
+              }
+            }
+            topd[(size_t)p * NT + tid] = d2;
+            topi[(size_t)p * NT + tid] = oi;
+            if (cnt < K) ++cnt;
+            if (cnt == K) {
+              worst = topd[(size_t)(K - 1) * NT + tid];
+              worst_i = topi[(size_t)(K - 1) * NT + tid];
+            }
+          }
+        }
+        __syncthreads();  // stage is overwritten by the next chunk
+      }
+    }
+
+    // ---- can this thread stop? distance from the target to the nearest open face of the block ----
+    bool done = true;
+    if (active && !whole) {
+      double margin = INFINITY;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        if (d < dim) {
+          if (nb0[d] > 0) margin = fmin(margin, tc[d] - (bn.lo[d] + nb0[d] * bn.cell[d]));
+          if (nb1[d] < bn.nb[d] - 1) margin = fmin(margin, (bn.lo[d] + (nb1[d] + 1) * bn.cell[d]) - tc[d]);
+        }
+      }
+      margin -= slack;
+      double safe2 = (margin > 0.0) ? margin * margin : 0.0;
+      done = (cnt == K && worst < safe2) || (safe2 > r2);
+    }
+    if (whole || __syncthreads_and(done ? 1 : 0)) break;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      ob0[d] = nb0[d];
+      ob1[d] = nb1[d];
+      mg[d] += max(1, mg[d] / 2);
+    }
+    have_old = true;
+  }
+
+  // ---- emit: ascending (d², idx); ball search keeps sqrt(d²) <= radius (inclusive) ----
+  if (active) {
+    int nn = cnt;
+    if (a.use_ball) {
+      nn = 0;
+      while (nn < cnt && sqrt(topd[(size_t)nn * NT + tid]) <= a.radius) ++nn;
+    }
+    const long long t = lin - a.first;
+    a.nn[t] = nn;
+    int *out = a.nbr + t * K;
+    for (int i = 0; i < K; ++i) out[i] = (i < nn) ? topi[(size_t)i * NT + tid] : -1;
+  }
+}
+
+}  // namespace
+
+int gsk_launch_search(gsk_ctx *ctx, long long first, long long count, int *d_nn, int *d_nbr, int *launches) {
+  GskSearchArgs a{};
+  a.tg = ctx->tg;
+  a.bins = ctx->bins;
+  a.k = ctx->prob.max_neighbors;
+  a.use_ball = !(ctx->prob.ball_radius != ctx->prob.ball_radius);
+  a.radius = a.use_ball ? ctx->prob.ball_radius : 0.0;
+  a.first = first;
+  a.count = count;
+  a.nn = d_nn;
+  a.nbr = d_nbr;
+  for (int d = 0; d < 3; ++d) a.margin0[d] = ctx->margin0[d];
+  const size_t smem = sizeof(double4) * SCAP + (size_t)a.k * NT * (sizeof(double) + sizeof(int));
+  const int dim = ctx->tg.dim;
+  unsigned nblocks;
+  int tile[3] = {NT, 1, 1};
+  if (dim == 2) { tile[0] = 16; tile[1] = 8; }
+  if (dim == 3) { tile[0] = 8; tile[1] = 4; tile[2] = 4; }
+  if (ctx->tg.is_grid) {
+    // bounding box of the slab in cell coordinates: whole rows/planes except along the slowest axis
+    long long gd[3] = {ctx->tg.gdim[0], ctx->tg.gdim[1], ctx->tg.gdim[2]};
+    long long last = first + count - 1;
+    long long lo[3] = {0, 0, 0}, hi[3] = {gd[0] - 1, gd[1] - 1, gd[2] - 1};
+    int slow = dim - 1;
+    long long stride = 1;
+    for (int d = 0; d < slow; ++d) stride *= gd[d];
+    lo[slow] = first / stride;
+    hi[slow] = last / stride;
+    if (lo[slow] == hi[slow] && slow > 0) {  // slab inside one plane/row: tighten the next axis too
+      long long s2 = stride / gd[slow - 1];
+      lo[slow - 1] = (first % stride) / s2;
+      hi[slow - 1] = (last % stride) / s2;
+    }
+    long long nt = 1;
+    for (int d = 0; d < 3; ++d) {
+      a.t0[d] = lo[d];
+      a.ntile[d] = (int)((hi[d] - lo[d] + tile[d]) / tile[d]);
+      nt *= a.ntile[d];
+    }
+    nblocks = (unsigned)nt;
+  } else {
+    nblocks = (unsigned)((count + NT - 1) / NT);
+  }
+  cudaError_t e;
+  if (dim == 1) {
+    e = cudaFuncSetAttribute(search_kernel<NT, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) search_kernel<NT, 1, 1><<<nblocks, NT, smem, ctx->stream>>>(a);
+  } else if (dim == 2) {
+    e = cudaFuncSetAttribute(search_kernel<16, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) search_kernel<16, 8, 1><<<nblocks, NT, smem, ctx->stream>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(search_kernel<8, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) search_kernel<8, 4, 4><<<nblocks, NT, smem, ctx->stream>>>(a);
+  }
+  GSK_CUDA_CHECK(ctx, e);
+  GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  if (launches) *launches += 1;
+  return GSK_OK;
+}
