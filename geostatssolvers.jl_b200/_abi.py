@@ -238,6 +238,8 @@ def load_library(path: os.PathLike | None = None):
     lib.gsk_execute.restype = C.c_int
     lib.gsk_get_timing.argtypes = [ctx, C.POINTER(GskTiming)]
     lib.gsk_get_timing.restype = C.c_int
+    lib.gsk_set_phase_timing.argtypes = [ctx, C.c_int]
+    lib.gsk_set_phase_timing.restype = C.c_int
     lib.gsk_num_targets.argtypes = [pp]
     lib.gsk_num_targets.restype = C.c_int64
     lib.gsk_uk_exponents.argtypes = [C.c_int, C.c_int, _ip, C.c_int]
@@ -255,7 +257,7 @@ def load_library(path: os.PathLike | None = None):
 
 EXPORTED_SYMBOLS = [
     "gsk_create", "gsk_destroy", "gsk_last_error", "gsk_set_stream", "gsk_synchronize", "gsk_krige", "gsk_plan",
-    "gsk_execute", "gsk_get_timing", "gsk_num_targets", "gsk_uk_exponents", "gsk_default_support",
+    "gsk_execute", "gsk_get_timing", "gsk_set_phase_timing", "gsk_num_targets", "gsk_uk_exponents", "gsk_default_support",
     "gsk_measure_fp64_peak", "gsk_abi_version",
 ]
 
@@ -325,6 +327,9 @@ class Context:
 
     def set_stream(self, cuda_stream: int):
         self._check(self.lib.gsk_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def set_phase_timing(self, on: bool):
+        self._check(self.lib.gsk_set_phase_timing(self._h, int(bool(on))))
 
     def synchronize(self):
         self._check(self.lib.gsk_synchronize(self._h))

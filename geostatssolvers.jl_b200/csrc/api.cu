@@ -23,9 +23,9 @@ static int fail(gsk_ctx *ctx, int code, const std::string &msg) {
 // ---------------------------------------------------------------------------------------------
 // host helpers
 // ---------------------------------------------------------------------------------------------
-extern "C" int gsk_abi_version(void) { return GSK_ABI_VERSION; }
+extern "C" GSK_API int gsk_abi_version(void) { return GSK_ABI_VERSION; }
 
-extern "C" int64_t gsk_num_targets(const gsk_problem *p) {
+extern "C" GSK_API int64_t gsk_num_targets(const gsk_problem *p) {
   if (!p) return -1;
   if (p->grid_dims[0] > 0) {
     int64_t t = 1;
@@ -37,7 +37,7 @@ extern "C" int64_t gsk_num_targets(const gsk_problem *p) {
 
 // GeoStatsModels' UKexps [3P]: exponent vectors of total degree 0..degree (each degree in descending
 // lexicographic order), stably sorted by descending max exponent → degree 1: x, y, (z), 1.
-extern "C" int gsk_uk_exponents(int degree, int dim, int32_t *out, int cap) {
+extern "C" GSK_API int gsk_uk_exponents(int degree, int dim, int32_t *out, int cap) {
   if (degree < 0 || degree > 2 || dim < 1 || dim > 3 || !out) return GSK_ERR_INVALID;
   int tmp[16][3];
   int n = 0;
@@ -63,7 +63,7 @@ extern "C" int gsk_uk_exponents(int degree, int dim, int32_t *out, int cap) {
 
 // Variography's geometry sub-sampling for γ(cell, point) [3P, SURVEY V1]: per axis
 // n = ceil(side / (min(range, min side)/3)) points at parametric positions j/(n+1), j = 1..n.
-extern "C" int gsk_default_support(int dim, const double *spacing, double vario_range, double *ox, double *oy,
+extern "C" GSK_API int gsk_default_support(int dim, const double *spacing, double vario_range, double *ox, double *oy,
                                    double *oz, int cap) {
   if (dim < 1 || dim > 3 || !spacing || !ox) return GSK_ERR_INVALID;
   double lmin = INFINITY;
@@ -94,7 +94,7 @@ extern "C" int gsk_default_support(int dim, const double *spacing, double vario_
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
-extern "C" int gsk_create(gsk_ctx **out, int device_id) {
+extern "C" GSK_API int gsk_create(gsk_ctx **out, int device_id) {
   if (!out) return fail(nullptr, GSK_ERR_INVALID, "gsk_create: out is NULL");
   *out = nullptr;
   int ndev = 0;
@@ -135,7 +135,7 @@ static void free_plan(gsk_ctx *ctx) {
   ctx->planned = false;
 }
 
-extern "C" void gsk_destroy(gsk_ctx *ctx) {
+extern "C" GSK_API void gsk_destroy(gsk_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -150,9 +150,9 @@ extern "C" void gsk_destroy(gsk_ctx *ctx) {
   delete ctx;
 }
 
-extern "C" const char *gsk_last_error(const gsk_ctx *ctx) { return ctx ? ctx->err.c_str() : g_static_err.c_str(); }
+extern "C" GSK_API const char *gsk_last_error(const gsk_ctx *ctx) { return ctx ? ctx->err.c_str() : g_static_err.c_str(); }
 
-extern "C" int gsk_set_stream(gsk_ctx *ctx, void *cuda_stream) {
+extern "C" GSK_API int gsk_set_stream(gsk_ctx *ctx, void *cuda_stream) {
   if (!ctx) return GSK_ERR_INVALID;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -162,7 +162,7 @@ extern "C" int gsk_set_stream(gsk_ctx *ctx, void *cuda_stream) {
   return GSK_OK;
 }
 
-extern "C" int gsk_synchronize(gsk_ctx *ctx) {
+extern "C" GSK_API int gsk_synchronize(gsk_ctx *ctx) {
   if (!ctx) return GSK_ERR_INVALID;
   GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -210,7 +210,7 @@ static int validate(gsk_ctx *ctx, const gsk_problem *p) {
   return GSK_OK;
 }
 
-extern "C" int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) {
+extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) {
   if (!ctx) return GSK_ERR_INVALID;
   int rc = validate(ctx, p);
   if (rc != GSK_OK) return rc;
@@ -326,14 +326,14 @@ static long long local_chunk_targets() {
   return v;
 }
 
-extern "C" int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count, double *d_mean, double *d_var,
+extern "C" GSK_API int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count, double *d_mean, double *d_var,
                            int32_t *d_nneigh, int32_t *d_neigh_idx) {
   if (!ctx) return GSK_ERR_INVALID;
   if (!ctx->planned) return fail(ctx, GSK_ERR_STATE, "gsk_execute called before gsk_plan");
   if (first < 0 || count < 0 || first + count > ctx->n_targets) return fail(ctx, GSK_ERR_INVALID, "target range out of bounds");
   if (!d_mean || !d_var) return fail(ctx, GSK_ERR_INVALID, "output buffers are NULL");
   GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
-  static const bool phase_timing = getenv("GSK_PHASE_TIMING") != nullptr;
+  const bool phase_timing = ctx->phase_timing;
   int launches = 0;
   double ms_search = 0.0, ms_solve = 0.0;
   GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -382,7 +382,13 @@ extern "C" int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count, double *d
   return GSK_OK;
 }
 
-extern "C" int gsk_get_timing(const gsk_ctx *cctx, gsk_timing *out) {
+extern "C" GSK_API int gsk_set_phase_timing(gsk_ctx *ctx, int on) {
+  if (!ctx) return GSK_ERR_INVALID;
+  ctx->phase_timing = on != 0;
+  return GSK_OK;
+}
+
+extern "C" GSK_API int gsk_get_timing(const gsk_ctx *cctx, gsk_timing *out) {
   gsk_ctx *ctx = const_cast<gsk_ctx *>(cctx);
   if (!ctx || !out) return GSK_ERR_INVALID;
   if (ctx->timing_pending) {
@@ -400,7 +406,7 @@ extern "C" int gsk_get_timing(const gsk_ctx *cctx, gsk_timing *out) {
 // ---------------------------------------------------------------------------------------------
 // one-shot host-buffer call: plan + execute + copies
 // ---------------------------------------------------------------------------------------------
-extern "C" int gsk_krige(gsk_ctx *ctx, const gsk_problem *p, double *mean_out, double *var_out, int32_t *nneigh_out,
+extern "C" GSK_API int gsk_krige(gsk_ctx *ctx, const gsk_problem *p, double *mean_out, double *var_out, int32_t *nneigh_out,
                          int32_t *neigh_idx_out) {
   if (!ctx) return GSK_ERR_INVALID;
   if (!mean_out || !var_out) return fail(ctx, GSK_ERR_INVALID, "mean_out / var_out are NULL");
@@ -438,7 +444,7 @@ extern "C" int gsk_krige(gsk_ctx *ctx, const gsk_problem *p, double *mean_out, d
   return GSK_OK;
 }
 
-extern "C" int gsk_measure_fp64_peak(gsk_ctx *ctx, double *dfma_tflops, double *dmma_tflops) {
+extern "C" GSK_API int gsk_measure_fp64_peak(gsk_ctx *ctx, double *dfma_tflops, double *dmma_tflops) {
   if (!ctx || !dfma_tflops || !dmma_tflops) return GSK_ERR_INVALID;
   GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   return gsk_peak_measure(ctx, dfma_tflops, dmma_tflops);

@@ -128,6 +128,7 @@ struct gsk_ctx {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   gsk_timing timing{};
   bool timing_pending = false;
+  bool phase_timing = false;
 };
 
 // bins.cu

@@ -31,6 +31,12 @@ extern "C" {
 
 #define GSK_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define GSK_API __attribute__((visibility("default")))
+#else
+#define GSK_API
+#endif
+
 /* ---- enumerations (values are ABI) ------------------------------------------------ */
 
 /* variogram family — ref call site: test/estimation/krig.jl:10 (GaussianVariogram(range=35.0, nugget=0.0));
@@ -125,16 +131,16 @@ typedef struct gsk_timing {
 } gsk_timing;
 
 /* ---- context ---------------------------------------------------------------------- */
-int gsk_create(gsk_ctx **out, int device_id);
-void gsk_destroy(gsk_ctx *ctx);
+GSK_API int gsk_create(gsk_ctx **out, int device_id);
+GSK_API void gsk_destroy(gsk_ctx *ctx);
 /* NUL-terminated, owned by ctx (or static when ctx == NULL), valid until the next call on ctx */
-const char *gsk_last_error(const gsk_ctx *ctx);
+GSK_API const char *gsk_last_error(const gsk_ctx *ctx);
 /* run all work of this context on the caller's CUDA stream (cudaStream_t passed as void*) */
-int gsk_set_stream(gsk_ctx *ctx, void *cuda_stream);
-int gsk_synchronize(gsk_ctx *ctx);
+GSK_API int gsk_set_stream(gsk_ctx *ctx, void *cuda_stream);
+GSK_API int gsk_synchronize(gsk_ctx *ctx);
 
 /* ---- one-shot, host buffers: replaces exactsolve / approxsolve (krig.jl:166,188) --- */
-int gsk_krige(gsk_ctx *ctx, const gsk_problem *prob,
+GSK_API int gsk_krige(gsk_ctx *ctx, const gsk_problem *prob,
               double *mean_out, double *var_out, /* length = slab target count */
               int32_t *nneigh_out,               /* optional: neighbours used per target (global: n_samples) */
               int32_t *neigh_idx_out);           /* optional: count × max_neighbors, 0-based, sorted by (d², idx), −1 padded */
@@ -143,29 +149,32 @@ int gsk_krige(gsk_ctx *ctx, const gsk_problem *prob,
  *      (krig.jl:110,117; fit at krig.jl:176) and then the per-target loops ------------- */
 /* uploads samples, builds the bin structure (local) or assembles + factorises the
  * global system (max_neighbors == 0); keeps everything resident in HBM */
-int gsk_plan(gsk_ctx *ctx, const gsk_problem *prob);
+GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *prob);
 /* computes targets [first, first+count) of the planned problem into DEVICE buffers;
  * asynchronous on the context stream */
-int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count,
+GSK_API int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count,
                 double *d_mean, double *d_var, int32_t *d_nneigh, int32_t *d_neigh_idx);
-int gsk_get_timing(const gsk_ctx *ctx, gsk_timing *out);
+GSK_API int gsk_get_timing(const gsk_ctx *ctx, gsk_timing *out);
+/* when on, gsk_execute brackets every search / solve launch with CUDA events (and synchronises on them)
+ * so that gsk_timing.ms_search / ms_solve are filled; off by default (no synchronisation in gsk_execute) */
+GSK_API int gsk_set_phase_timing(gsk_ctx *ctx, int on);
 
 /* ---- host helpers shared by every binding ------------------------------------------ */
 /* number of targets of the problem's domain (grid product or n_points) */
-int64_t gsk_num_targets(const gsk_problem *prob);
+GSK_API int64_t gsk_num_targets(const gsk_problem *prob);
 /* Universal-Kriging monomial exponents in the reference's order (GeoStatsModels UKexps:
  * descending max exponent, stable, constant term last). out: dim × nterms, term-major
  * (out[t*dim + d]); returns nterms or a negative error */
-int gsk_uk_exponents(int degree, int dim, int32_t *out, int out_capacity_terms);
+GSK_API int gsk_uk_exponents(int degree, int dim, int32_t *out, int out_capacity_terms);
 /* default block support of a grid cell: per axis
  * n = ceil(side / (min(range, min side)/3)), offsets (j/(n+1) − 1/2)·side, j = 1..n.
  * Writes x-fastest tensor-product offsets; returns n_support or a negative error */
-int gsk_default_support(int dim, const double *spacing, double vario_range,
+GSK_API int gsk_default_support(int dim, const double *spacing, double vario_range,
                         double *off_x, double *off_y, double *off_z, int capacity);
 /* measured FP64 peaks of the context's device (roofline denominators): a dependent-free
  * DFMA loop and an mma.sync m8n8k4 f64 (DMMA) loop, TFLOP/s */
-int gsk_measure_fp64_peak(gsk_ctx *ctx, double *dfma_tflops, double *dmma_tflops);
-int gsk_abi_version(void);
+GSK_API int gsk_measure_fp64_peak(gsk_ctx *ctx, double *dfma_tflops, double *dmma_tflops);
+GSK_API int gsk_abi_version(void);
 
 #ifdef __cplusplus
 }

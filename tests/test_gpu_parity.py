@@ -1,0 +1,257 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (libgskrige.so via ctypes), against
+the CPU oracle on identical inputs — neighbour sets bit-exact, mean/variance rtol 1e-9 (Float64),
+plus the reference's own known-answer checks through the mirrored `solve` API and the committed
+golden vectors. Sizes are such that the oracle finishes in seconds; BASELINE-size cases are checked
+on random target subsets and through size-independent properties."""
+import numpy as np
+import pytest
+
+from _cases import CASES, GOLDEN, build_case, ref_problem_1d, ref_problem_2d
+from conftest import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(ctx, oracle, spec, search=None):
+    search = oracle.SEARCH_KDTREE if search is None else search
+    g = ctx.krige(spec, want_neighbors=True)
+    o = oracle.krige(spec, search=search, want_neighbors=True)
+    return g, o
+
+
+def _check(gsk, ctx, oracle, spec, **tol):
+    (mean, var, nn, idx), (om, ov, onn, oidx) = _both(ctx, oracle, spec)
+    assert np.array_equal(nn, onn)
+    if spec.params["max_neighbors"] > 0:
+        assert np.array_equal(idx, oidx)          # bit-exact neighbour sets, sorted by (d², idx)
+    assert_parity(mean, var, om, ov, scale=max(1.0, np.abs(spec.values).max()), sill=spec.params["vario_sill"], **tol)
+    return mean, var
+
+
+# ---- the reference's own tests, through the mirrored public API (test/estimation/krig.jl) ----
+def test_reference_testset_through_solve(gsk, ctx):
+    g35 = gsk.GaussianVariogram(range=35.0, nugget=0.0)
+    data1d = gsk.georef({"z": [0.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.4, 0.3, 0.2, 0.1, 0.0]}, np.arange(0.0, 101.0, 10.0)[None, :])
+    prob1d = gsk.EstimationProblem(data1d, gsk.CartesianGrid(100), "z")
+    for params in (dict(variogram=g35), dict(variogram=g35, maxneighbors=3),
+                   dict(variogram=g35, maxneighbors=3, neighborhood=gsk.MetricBall(100.0))):
+        sol = gsk.solve(prob1d, gsk.KrigingSolver(z=params), ctx=ctx)               # krig.jl:6-19 (smoke)
+        assert np.all(np.isfinite(np.asarray(sol.z))) and np.all(np.asarray(sol["z_variance"]) >= 0)
+    data2d = gsk.georef({"z": [1.0, 0.0, 1.0]}, [(25.0, 25.0), (50.0, 75.0), (75.0, 50.0)])
+    grid2d = gsk.CartesianGrid((100, 100), (0.5, 0.5), (1.0, 1.0))
+    prob2d = gsk.EstimationProblem(data2d, grid2d, "z")
+    for params in (dict(variogram=g35), dict(variogram=g35, maxneighbors=3),
+                   dict(variogram=g35, maxneighbors=3, neighborhood=gsk.MetricBall(100.0)),
+                   dict(variogram=g35, maxneighbors=3, neighborhood=gsk.MetricBall(100.0), path=gsk.MultiGridPath())):
+        sol = gsk.solve(prob2d, gsk.KrigingSolver(z=params), ctx=ctx)
+        Z = gsk.asarray(sol, "z")
+        S = np.asarray(sol.z)
+        for i, j, expected in GOLDEN["ref_checks"]:
+            i, j = int(i), int(j)
+            assert abs(Z[i - 1, j - 1] - expected) < 1e-3                          # krig.jl:35-37,50-52
+            assert abs(S[(i - 1) + (j - 1) * 100] - expected) < 1e-3               # krig.jl:70-72 (LinearIndices)
+
+
+@pytest.mark.parametrize("k,radius", [(0, None), (3, None), (3, 100.0)])
+def test_reference_problems_vs_oracle(gsk, ctx, oracle, k, radius):
+    _check(gsk, ctx, oracle, ref_problem_2d(gsk, k, radius), atol_mean=1e-11, atol_var=1e-11)
+    _check(gsk, ctx, oracle, ref_problem_1d(gsk, k, radius), atol_mean=1e-7, atol_var=1e-9)  # 11 Gaussian samples at h/r=0.29: cond ~1e9
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_golden_vectors(gsk, ctx, case):
+    name = case[0]
+    spec = build_case(case)
+    mean, var, nn, idx = ctx.krige(spec, want_neighbors=True)
+    assert np.array_equal(nn, GOLDEN[f"{name}/nn"])
+    if spec.params["max_neighbors"] > 0:
+        assert np.array_equal(idx, GOLDEN[f"{name}/idx"])
+    gauss = spec.params["vario_kind"] == gsk.VARIO_GAUSSIAN
+    assert_parity(mean, var, GOLDEN[f"{name}/mean"], GOLDEN[f"{name}/var"], scale=np.abs(spec.values).max(),
+                  atol_mean=2e-8 if gauss else None, atol_var=2e-9 if gauss else None)
+
+
+# ---- BASELINE.json configs at oracle-friendly sizes ----
+@pytest.mark.parametrize("name,scale", [("C2", 0.25), ("C3a", 0.16), ("C3b", 0.16), ("C5", 0.07)])
+def test_local_configs_scaled(gsk, ctx, oracle, name, scale):
+    _check(gsk, ctx, oracle, gsk.synth.config_spec(name, scale=scale))
+
+
+def test_config_c1_full(gsk, ctx, oracle):
+    """C1 at full size (500 samples → 100×100, global OK, Gaussian r=35). cond(C) ≈ 6e7 with the 1e-6
+    nugget, so any two backward-stable solvers differ by ~cond·eps·|z| ≈ 1e-8 in the mean (LU vs
+    Bunch–Kaufman vs long double: see DESIGN.md §Numerics); the floor below is that bound."""
+    _check(gsk, ctx, oracle, gsk.synth.config_spec("C1"), atol_mean=2e-8, atol_var=1e-10)
+
+
+def test_config_c4_reduced(gsk, ctx, oracle):
+    """C4's shape (global OK, Spherical r=256) at n=1500 onto 96×96 — well conditioned → strict rtol."""
+    _check(gsk, ctx, oracle, gsk.synth.config_spec("C4", grid=(96, 96), n=1500))
+
+
+def test_config_c2_full_size_subset_and_properties(gsk, ctx, oracle):
+    """C2 at BASELINE size (1e4 samples → 1000×1000, k=20): parity on 3 random row slabs, and
+    size-independent properties on the whole field."""
+    spec = gsk.synth.config_spec("C2")
+    mean, var, nn, idx = ctx.krige(spec, want_neighbors=True)
+    assert mean.shape == (1_000_000,) and np.all(nn == 20)
+    assert np.all(np.isfinite(mean)) and np.all(var >= 0) and np.all(var <= 1.0 + 1e-9)
+    assert np.all((idx >= 0) & (idx < spec.n_samples))
+    assert np.all(np.sort(idx, axis=1)[:, 1:] != np.sort(idx, axis=1)[:, :-1])      # no duplicate neighbour
+    # distances of the reported neighbours are ascending
+    ctr = spec.target_centers()
+    sub = np.random.default_rng(5).choice(spec.n_targets, 20000, replace=False)
+    dx = spec.coords[0][idx[sub]] - ctr[0][sub, None]
+    dy = spec.coords[1][idx[sub]] - ctr[1][sub, None]
+    d2 = dx * dx + dy * dy
+    assert np.all(np.diff(d2, axis=1) >= 0)
+    for first in (0, 333_000, 990_000):
+        slab = spec.with_slab(first, 10_000)
+        om, ov, onn, oidx = oracle.krige(slab, want_neighbors=True)
+        assert np.array_equal(idx[first:first + 10_000], oidx)
+        assert_parity(mean[first:first + 10_000], var[first:first + 10_000], om, ov, scale=2.0)
+    # Ordinary Kriging is exact for constants: shifting z by c shifts the mean by c, variance unchanged
+    shifted = gsk.synth.config_spec("C2")
+    shifted.values = shifted.values + 7.5
+    m2, v2 = ctx.krige(shifted.with_slab(500_000, 50_000))
+    np.testing.assert_allclose(m2, mean[500_000:550_000] + 7.5, rtol=1e-12, atol=1e-12)
+    np.testing.assert_array_equal(v2, var[500_000:550_000])
+
+
+# ---- estimator × variogram × dimension matrix ----
+@pytest.mark.parametrize("dim", [1, 2, 3])
+@pytest.mark.parametrize("vk", [0, 1, 2])
+@pytest.mark.parametrize("est,deg", [(0, 0), (1, 0), (2, 1), (2, 2)])
+def test_matrix(gsk, ctx, oracle, dim, vk, est, deg):
+    grid = {1: (300,), 2: (24, 20), 3: (10, 9, 8)}[dim]
+    n = {1: 60, 2: 150, 3: 260}[dim]
+    k = 10 if est == 2 and deg == 2 and dim == 3 else 8
+    k = {1: 6, 2: k + 4, 3: k + 8}[dim]
+    coords, vals = gsk.synth.make_samples(100 + dim, n, grid, seed_extra=vk * 10 + est)
+    rng = {1: 40.0, 2: 9.0, 3: 6.0}[dim]
+    spec = gsk.ProblemSpec(coords=coords, values=vals, grid_dims=grid, support=gsk.default_support_py([1.0] * dim, rng),
+                           vario_kind=vk, vario_range=rng, vario_sill=1.3, vario_nugget=0.05, estimator=est,
+                           uk_degree=deg, sk_mean=float(vals.mean()), max_neighbors=k)
+    loose = vk == 0 or (est == 2 and deg == 2)    # Gaussian / quadratic drift in raw coordinates: cond ≳ 1e6
+    _check(gsk, ctx, oracle, spec, **(dict(atol_mean=1e-7, atol_var=1e-7) if loose else {}))
+
+
+# ---- edge cases ----
+def test_ball_and_min_neighbors_produce_missing(gsk, ctx, oracle):
+    spec = gsk.synth.config_spec("C2", scale=0.2, ball_radius=9.0, min_neighbors=4)
+    mean, var = _check(gsk, ctx, oracle, spec)
+    assert np.isnan(mean).any() and (~np.isnan(mean)).any()
+    spec3 = gsk.synth.config_spec("C3a", scale=0.12, ball_radius=7.0, min_neighbors=3)
+    _check(gsk, ctx, oracle, spec3)
+
+
+def test_point_targets_point_support(gsk, ctx, oracle):
+    base = gsk.synth.config_spec("C2", scale=0.1)
+    rng = np.random.default_rng(3)
+    pts = [rng.uniform(-5, 105, 5000), rng.uniform(-5, 105, 5000)]   # unordered, partly outside the samples' box
+    spec = gsk.ProblemSpec(coords=base.coords, values=base.values, points=pts, vario_kind=gsk.VARIO_SPHERICAL,
+                           vario_range=50.0, max_neighbors=12)
+    _check(gsk, ctx, oracle, spec)
+    # targets ON samples (point support, nugget 0): exact interpolation, zero variance
+    on = gsk.ProblemSpec(coords=base.coords, values=base.values, points=[c[:200] for c in base.coords],
+                         vario_kind=gsk.VARIO_SPHERICAL, vario_range=50.0, max_neighbors=12)
+    mean, var = ctx.krige(on)
+    np.testing.assert_allclose(mean, base.values[:200], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(var, 0.0, atol=1e-9)
+    glob = ctx.krige(gsk.ProblemSpec(coords=[c[:300] for c in base.coords], values=base.values[:300],
+                                     points=[c[:50] for c in base.coords], vario_kind=gsk.VARIO_EXPONENTIAL,
+                                     vario_range=30.0, max_neighbors=0))
+    np.testing.assert_allclose(glob[0], base.values[:50], rtol=0, atol=1e-8)
+
+
+def test_small_and_degenerate_inputs(gsk, ctx, oracle):
+    # k = n (host clamp), k = 1, a single sample, collinear samples, far-away coordinates
+    coords = [np.array([1.0, 4.0, 9.0, 2.5]), np.array([2.0, 2.0, 2.0, 2.0])]
+    vals = np.array([0.3, 1.1, -0.4, 0.9])
+    for k in (1, 2, 4):
+        spec = gsk.ProblemSpec(coords=coords, values=vals, grid_dims=(12, 5), vario_kind=gsk.VARIO_EXPONENTIAL,
+                               vario_range=5.0, max_neighbors=k)
+        _check(gsk, ctx, oracle, spec)
+    one = gsk.ProblemSpec(coords=[np.array([3.0])], values=np.array([2.0]), grid_dims=(7,), vario_kind=gsk.VARIO_SPHERICAL,
+                          vario_range=4.0, max_neighbors=1)
+    _check(gsk, ctx, oracle, one)
+    big = gsk.synth.config_spec("C2", scale=0.1)
+    big.coords = [c + 4.0e6 for c in big.coords]
+    big.grid_origin = [4.0e6, 4.0e6]
+    _check(gsk, ctx, oracle, big)
+    empty = gsk.synth.config_spec("C2", scale=0.1).with_slab(10, 0)
+    m, v = ctx.krige(empty)
+    assert m.shape == (0,) and v.shape == (0,)
+
+
+def test_clustered_samples_exact_neighbours(gsk, ctx, oracle):
+    """Strongly non-uniform density: the ring expansion must still return the exact kNN."""
+    rng = np.random.default_rng(11)
+    c1 = rng.normal([20, 20], 1.5, (600, 2)); c2 = rng.normal([80, 70], 4.0, (300, 2)); c3 = rng.uniform(0, 100, (40, 2))
+    xy = np.concatenate([c1, c2, c3])
+    vals = np.sin(xy[:, 0] / 9.0) + 0.1 * rng.standard_normal(len(xy))
+    spec = gsk.ProblemSpec(coords=[xy[:, 0], xy[:, 1]], values=vals, grid_dims=(100, 100),
+                           support=gsk.default_support_py([1.0, 1.0], 30.0), vario_kind=gsk.VARIO_EXPONENTIAL,
+                           vario_range=30.0, vario_nugget=0.02, max_neighbors=16)
+    _check(gsk, ctx, oracle, spec)
+
+
+def test_ties_fall_to_lower_index(gsk, ctx, oracle):
+    """A regular sample lattice with targets on cell centres: many exactly tied distances."""
+    gx, gy = np.meshgrid(np.arange(0.0, 20.0, 2.0), np.arange(0.0, 20.0, 2.0), indexing="ij")
+    coords = [gx.ravel(), gy.ravel()]
+    vals = np.cos(coords[0]) + coords[1] * 0.1
+    spec = gsk.ProblemSpec(coords=coords, values=vals, grid_dims=(20, 20), grid_origin=(-0.5, -0.5),
+                           vario_kind=gsk.VARIO_SPHERICAL, vario_range=8.0, max_neighbors=6)
+    (mean, var, nn, idx), (om, ov, onn, oidx) = _both(ctx, oracle, spec, oracle.SEARCH_BRUTE)
+    assert np.array_equal(idx, oidx)
+
+
+# ---- sharding and the resident form ----
+def test_slabs_equal_full(gsk, ctx):
+    spec = gsk.synth.config_spec("C3a", scale=0.14)
+    full = ctx.krige(spec)
+    T = spec.n_targets
+    for world in (2, 3, 8):
+        parts = [ctx.krige(spec.with_slab(*gsk.slab_bounds(T, r, world))) for r in range(world)]
+        assert np.array_equal(np.concatenate([p[0] for p in parts]), full[0])
+        assert np.array_equal(np.concatenate([p[1] for p in parts]), full[1])
+
+
+def test_resident_plan_execute_matches_one_shot(gsk, ctx):
+    import torch
+    spec = gsk.synth.config_spec("C2", scale=0.2)
+    mean, var = ctx.krige(spec)
+    T = spec.n_targets
+    dm = torch.empty(T, dtype=torch.float64, device="cuda")
+    dv = torch.empty(T, dtype=torch.float64, device="cuda")
+    own = gsk.Context(0)
+    own.set_stream(torch.cuda.current_stream().cuda_stream)
+    own.plan(spec)
+    own.execute(0, T, dm.data_ptr(), dv.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(dm.cpu().numpy(), mean) and np.array_equal(dv.cpu().numpy(), var)
+    t = own.timing()
+    assert t["launches"] >= 2 and t["targets"] == T
+    with pytest.raises(gsk.GskError):
+        gsk.Context(0).execute(0, 1, dm.data_ptr(), dv.data_ptr())      # execute before plan
+    own.close()
+
+
+def test_invalid_arguments_are_rejected(gsk, ctx):
+    spec = gsk.synth.config_spec("C2", scale=0.1)
+    bad = gsk.synth.config_spec("C2", scale=0.1)
+    bad.params["max_neighbors"] = spec.n_samples + 1
+    with pytest.raises(gsk.GskError, match="clamped"):
+        ctx.krige(bad)
+    bad.params["max_neighbors"] = gsk.GSK_MAX_NEIGHBORS + 1
+    with pytest.raises(gsk.GskError):
+        ctx.krige(bad)
+    bad = gsk.synth.config_spec("C2", scale=0.1)
+    bad.params["vario_range"] = 0.0
+    with pytest.raises(gsk.GskError, match="vario_range"):
+        ctx.krige(bad)
+    bad = gsk.synth.config_spec("C2", scale=0.1)
+    bad.coords[0][3] = np.nan
+    with pytest.raises(gsk.GskError, match="finite"):
+        ctx.krige(bad)
