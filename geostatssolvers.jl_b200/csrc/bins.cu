@@ -5,6 +5,8 @@
 // shared memory.
 #include <math.h>
 
+#include <cmath>
+
 #include <algorithm>
 
 #include "gsk_internal.cuh"
@@ -110,11 +112,14 @@ int gsk_build_bins(gsk_ctx *ctx, const double *hx, const double *hy, const doubl
   double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
   for (int d = 0; d < dim; ++d) {
     double mn = h[d][0], mx = h[d][0];
-    for (long long i = 1; i < n; ++i) {
-      mn = std::min(mn, h[d][i]);
-      mx = std::max(mx, h[d][i]);
+    bool finite = true;
+    for (long long i = 0; i < n; ++i) {
+      const double v = h[d][i];
+      finite = finite && std::isfinite(v);
+      mn = std::min(mn, v);
+      mx = std::max(mx, v);
     }
-    if (!(mn == mn) || !(mx == mx) || isinf(mn) || isinf(mx)) {
+    if (!finite) {
       ctx->err = "sample coordinates must be finite";
       return GSK_ERR_INVALID;
     }

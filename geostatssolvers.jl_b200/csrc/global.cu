@@ -13,6 +13,8 @@
 //   ν = Gff⁻¹(Gfb − f₀),  mean = Gbz − Gfz·ν,  var = sill − (Gbb − Gfb·ν + f₀·ν)      (SK: μ + Gbz, sill − Gbb)
 #include <math.h>
 
+#include <cmath>
+
 #include <algorithm>
 #include <vector>
 
@@ -446,8 +448,13 @@ int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const doub
 
   // samples → {x,y,z,value} records
   std::vector<double4> rec((size_t)n);
-  for (long long i = 0; i < n; ++i)
+  for (long long i = 0; i < n; ++i) {
     rec[(size_t)i] = make_double4(hx[i], dim > 1 ? hy[i] : 0.0, dim > 2 ? hz[i] : 0.0, hv[i]);
+    if (!std::isfinite(rec[(size_t)i].x) || !std::isfinite(rec[(size_t)i].y) || !std::isfinite(rec[(size_t)i].z)) {
+      ctx->err = "sample coordinates must be finite";
+      return GSK_ERR_INVALID;
+    }
+  }
   GSK_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_rec_orig, sizeof(double4) * (size_t)n));
   GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_rec_orig, rec.data(), sizeof(double4) * (size_t)n, cudaMemcpyHostToDevice, st));
   GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));

@@ -28,8 +28,8 @@ int gsk_launch_local_solve(gsk_ctx *ctx, long long first, long long count, const
   if (rows(4) <= 12) err = gsk_local_launch_A(a, e, ctx->stream);
   else if (rows(4) <= 24) err = gsk_local_launch_B(a, e, ctx->stream);
   else if (rows(8) <= 40) err = gsk_local_launch_C(a, e, ctx->stream);
-  else if (rows(8) <= 80) err = gsk_local_launch_D(a, e, ctx->stream);
-  else if (rows(8) <= 128) err = gsk_local_launch_E(a, e, ctx->stream);
+  else if (rows(8) <= 72) err = gsk_local_launch_D(a, e, ctx->stream);
+  else if (rows(8) <= 112) err = gsk_local_launch_E(a, e, ctx->stream);
   else {
     ctx->err = "max_neighbors too large for the local kernels";
     return GSK_ERR_UNSUPPORTED;

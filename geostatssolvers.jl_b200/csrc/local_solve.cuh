@@ -15,9 +15,13 @@
 // elimination (C first, then the c×c Schur system) — no back substitution, no pivot search.
 //
 // Mapping: G lanes cooperate on one target (32/G targets per warp). Lane l owns rows l, l+G, …
-// (R register slots); the factor lives packed in shared memory (column p keeps rows ≥ p&~3) and
-// is built in place, W columns at a time: left-looking update from finished columns (own entries
-// + W broadcast entries per finished column → R·W independent DFMAs), then the W×W panel.
+// (R register slots, RT = R·G rows in total: KC neighbour rows padded to the panel width, then the
+// extra rows, then zero padding). The factor lives column-packed in shared memory (column p keeps
+// rows ≥ p rounded down to the panel alignment) and is built in place, W columns at a time:
+// left-looking update from the finished columns (own entries + W broadcast entries per finished
+// column → R·W independent DFMAs), then the W×W panel, whose pivots and row entries travel between
+// the lanes of the group by warp shuffles. The panel loop is unrolled with static column offsets,
+// so all shared-memory addressing is base + immediate.
 #pragma once
 #include <math.h>
 
@@ -25,76 +29,118 @@
 
 namespace gsk_local {
 
-constexpr int CTA_THREADS = 128;
+
+template <int W>
+__host__ __device__ constexpr int col_align() { return W == 8 ? 8 : 4; }
+
+// doubles stored before column p: Σ_{j<p} (RT − (j & ~(A−1)))
+template <int RT, int A>
+__host__ __device__ constexpr int col_off(int p) {
+  return p * RT - A * A * ((p / A) * ((p / A) - 1) / 2) - A * (p / A) * (p % A);
+}
 
 struct Layout {
-  int KC, EP, RT;    // padded neighbour columns, padded extra rows, total rows
-  int e;             // live extra rows
-  int stor;          // doubles of packed factor storage per target
-  int gsz;           // doubles per target group (all per-target shared memory)
-  int off_nb, off_v, off_b, off_s, off_gm, off_piv;
+  int KC;    // neighbour columns, padded to a multiple of W
+  int e;     // live extra rows (2 + c)
+  int EPr;   // e rounded up to a multiple of W
+  int gsz;   // doubles of shared memory per target group
+  int off_nb, off_gm;
 };
 
-__host__ __device__ inline int col_start_row(int p) { return p & ~3; }
-
-template <int DIM>
-__host__ inline Layout make_layout(int k, int e, int W) {
+template <int G, int R, int W, int RS, int DIM>
+__host__ inline Layout make_layout(int k, int e) {
+  constexpr int RT = RS, A = col_align<W>(), KCMAX = RT - W;
   Layout L;
   L.KC = (k + W - 1) / W * W;
-  L.EP = (e + W - 1) / W * W;
-  L.RT = L.KC + L.EP;
   L.e = e;
-  int stor = 0;
-  for (int p = 0; p < L.KC; ++p) stor += L.RT - col_start_row(p);
-  L.stor = stor;
-  int o = 0;
-  L.off_nb = o; o += DIM * L.KC;
-  L.off_v = o;  o += L.KC;
-  L.off_b = o;  o += L.KC;
-  L.off_s = o;  o += stor;       // all of the above are multiples of 4 doubles → 32-B aligned
-  L.off_gm = o; o += L.EP * L.EP;
-  L.off_piv = o; o += 4;
-  // spread the groups of a warp over the banks: make the stride ≡ 4 (mod 8) doubles
-  while ((o & 7) != 4) o += 4;
+  L.EPr = (e + W - 1) / W * W;
+  int o = col_off<RT, A>(KCMAX);  // factor storage (static maximum); multiple of 4 doubles
+  L.off_nb = o;
+  o += DIM * KCMAX;
+  L.off_gm = o;
+  o += L.EPr * L.EPr;
+  while ((o & 15) != 4 && (o & 15) != 12) o += 4;  // spread the groups of a warp over the banks
   L.gsz = o;
   return L;
 }
 
-template <int G, int R, int W, int DIM, int VK>
-__global__ void __launch_bounds__(CTA_THREADS) local_solve_kernel(const GskLocalArgs a, const Layout L) {
-  constexpr int TPW = 32 / G;                   // targets per warp
-  constexpr int TPC = TPW * (CTA_THREADS / 32);  // targets per CTA
+// 1/sqrt(d) to ~1 ulp: MUFU.RSQ64H seed (2^-22) + two Newton steps
+__device__ __forceinline__ double gsk_rsqrt(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double h = 0.5 * d;
+  double r = fma(-(h * y), y, 0.5);
+  y = fma(y, r, y);
+  r = fma(-(h * y), y, 0.5);
+  y = fma(y, r, y);
+  return y;
+}
+
+// sqrt(u) for u > 0 (u == 0 yields NaN, discarded by the callers' d2 > 0 select): coupled Goldschmidt
+__device__ __forceinline__ double gsk_sqrt_pos(double u) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u));
+  double g = u * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  g = fma(g, r, g);
+  return g;
+}
+
+// covariance from the squared distance, fast-path math (same formulas as gsk_cov)
+template <int VK>
+__device__ __forceinline__ double cov_fast(const GskVario &v, double d2) {
+  double c;
+  if (VK == GSK_VARIO_GAUSSIAN) {
+    c = v.cs * exp(-3.0 * d2 * v.inv_r2);
+  } else if (VK == GSK_VARIO_SPHERICAL) {
+    const double u = d2 * v.inv_r2;
+    const double t = gsk_sqrt_pos(u);
+    const double g = fma(t, fma(0.5, u, -1.5), 1.0);
+    c = (u < 1.0) ? v.cs * g : 0.0;
+  } else {
+    c = v.cs * exp(-3.0 * v.inv_r * gsk_sqrt_pos(d2));
+  }
+  return (d2 > 0.0) ? c : v.sill;
+}
+
+// G lanes per target, R register row slots (R·G >= RS), W panel width, RS rows stored per column,
+// NT threads per CTA
+template <int G, int R, int W, int RS, int NT, int DIM, int VK>
+__global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, const Layout L) {
+  static_assert(R * G >= RS && RS % W == 0, "register rows must cover the stored rows");
+  constexpr int CTA_THREADS = NT;
+  constexpr int RT = RS;
+  constexpr int A = col_align<W>();
+  constexpr int KCMAX = RT - W;
+  constexpr int TPW = 32 / G;
+  constexpr int TPC = TPW * (CTA_THREADS / 32);
+  constexpr bool UNROLL_P = (G == 4);  // small systems: unroll the left-looking loops completely
+  // register row r·G + l exists in storage (static except in the last, partially covered slot)
+#define GSK_ROW_OK(r) (((r) * G + G <= RS) || ((r) * G + l < RS))
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sm = reinterpret_cast<double *>(smem_raw);
-  // CTA-wide tables
-  double *sup = sm;                                     // [3][nsup]
-  int nsup_pad = (3 * a.nsup + 3) & ~3;
-  int *colOff = reinterpret_cast<int *>(sm + nsup_pad);  // [KC]
-  int coff_pad = ((L.KC + 1) / 2 + 3) & ~3;             // in doubles
-  double *groups = sm + nsup_pad + coff_pad;
+  double *sup = sm;  // [3][nsup]
+  const int nsup_pad = (3 * a.nsup + 3) & ~3;
+  double *groups = sm + nsup_pad;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int l = lane % G;                 // lane within the target group
-  const int grp = tid / G;                // group within the CTA
-  const int KC = L.KC, RT = L.RT, EP = L.EP, e = L.e;
+  const int l = lane % G;   // lane within the target group
+  const int grp = tid / G;  // group within the CTA
+  const int gbase = lane - l;  // first lane of my group in the warp
+  const int KC = L.KC, e = L.e, EPr = L.EPr;
 
   for (int i = tid; i < 3 * a.nsup; i += CTA_THREADS) sup[i] = a.sup[i];
-  if (tid == 0) {
-    int o = 0;
-    for (int p = 0; p < KC; ++p) { colOff[p] = o; o += RT - col_start_row(p); }
-  }
   __syncthreads();
 
-  double *gs = groups + (size_t)grp * L.gsz;
-  double *nbX = gs + L.off_nb;
-  double *nbY = nbX + KC;
-  double *nbZ = (DIM == 3) ? nbY + KC : nbY;
-  double *V = gs + L.off_v;
-  double *B = gs + L.off_b;
-  double *S = gs + L.off_s;
-  double *GM = gs + L.off_gm;
-  double *PIV = gs + L.off_piv;
+  double *S = groups + (size_t)grp * L.gsz;
+  double *nbX = S + L.off_nb;
+  double *nbY = nbX + KCMAX;
+  double *nbZ = (DIM == 3) ? nbY + KCMAX : nbY;
+  double *GM = S + L.off_gm;
 
   const long long t = (long long)blockIdx.x * TPC + grp;  // slab-local target
   const bool live = t < a.count;
@@ -123,179 +169,177 @@ __global__ void __launch_bounds__(CTA_THREADS) local_solve_kernel(const GskLocal
   const bool estimate = live && nn >= a.min_neighbors && nn > 0;
   if (!estimate) nn = 0;
 
-  // ---- phase 1: gather neighbours (coordinates + value in one 32-byte record) ----
-  for (int j = l; j < KC; j += G) {
-    double4 rc = make_double4(0.0, 0.0, 0.0, 0.0);
-    if (j < nn) {
-      int idx = a.nbr[t * a.k + j];
-      rc = a.rec_orig[idx];
-    }
-    nbX[j] = rc.x;
-    nbY[j] = rc.y;
-    if (DIM == 3) nbZ[j] = rc.z;
-    V[j] = (j < nn) ? ((a.es.kind == GSK_EST_SIMPLE) ? rc.w - a.es.sk_mean : rc.w) : 0.0;
-  }
-  __syncwarp();
-
-  // ---- phase 2: block-support right-hand side  b_j = mean_q C(‖t + δ_q − x_j‖) ----
+  // ---- phase 1+2: gather neighbours; block-support RHS b_j = mean_q C(‖t + δ_q − x_j‖); extra rows ----
   {
     const double inv_q = 1.0 / (double)a.nsup;
+    const int nextra = RT - KC;
     for (int j = l; j < KC; j += G) {
+      const bool valid = j < nn;
+      double4 rc = make_double4(0.0, 0.0, 0.0, 0.0);
+      if (valid) rc = a.rec_orig[a.nbr[t * a.k + j]];
+      nbX[j] = rc.x;
+      nbY[j] = rc.y;
+      if (DIM == 3) nbZ[j] = rc.z;
       double acc = 0.0;
-      if (j < nn) {
-        const double xj = nbX[j], yj = nbY[j], zj = (DIM == 3) ? nbZ[j] : 0.0;
+      if (valid) {
         for (int q = 0; q < a.nsup; ++q) {
-          double dx = (tc[0] + sup[q]) - xj;
-          double dy = (tc[1] + sup[a.nsup + q]) - yj;
+          const double dx = (tc[0] + sup[q]) - rc.x;
+          const double dy = (tc[1] + sup[a.nsup + q]) - rc.y;
           double d2 = fma(dy, dy, dx * dx);
           if (DIM == 3) {
-            double dz = (tc[2] + sup[2 * a.nsup + q]) - zj;
+            const double dz = (tc[2] + sup[2 * a.nsup + q]) - rc.z;
             d2 = fma(dz, dz, d2);
           }
-          acc += gsk_cov<VK>(vg, d2);
+          acc += cov_fast<VK>(vg, d2);
         }
       }
-      B[j] = acc * inv_q;
+      double *colj = S + col_off<RT, A>(j) - (j & ~(A - 1));
+      colj[KC] = acc * inv_q;
+      colj[KC + 1] = valid ? ((a.es.kind == GSK_EST_SIMPLE) ? rc.w - a.es.sk_mean : rc.w) : 0.0;
+      for (int r2 = 2; r2 < nextra; ++r2) {
+        double v = 0.0;
+        if (valid && r2 < e) {
+          if (a.es.kind == GSK_EST_ORDINARY) v = 1.0;
+          else {
+            const int *ex = a.es.exps[r2 - 2];
+            v = gsk_ipow(rc.x, ex[0]) * gsk_ipow(rc.y, ex[1]);
+            if (DIM == 3) v *= gsk_ipow(rc.z, ex[2]);
+          }
+        }
+        colj[KC + r2] = v;
+      }
     }
   }
   __syncwarp();
 
-  // ---- phase 3: fill the augmented matrix in place (column p, rows >= p&~3) ----
+  // ---- phase 3: covariance block in place (column p, neighbour rows >= p & ~(A−1)) ----
   for (int p = 0; p < KC; ++p) {
     const bool valid_p = p < nn;
     const double xp = nbX[p], yp = nbY[p], zp = (DIM == 3) ? nbZ[p] : 0.0;
-    const int sp = col_start_row(p);
-    double *col = S + colOff[p] - sp;
-    for (int i = sp + l; i < RT; i += G) {
+    const int sp = p & ~(A - 1);
+    double *col = S + col_off<RT, A>(p) - sp;
+    for (int i = sp + l; i < KC; i += G) {
       double v = 0.0;
-      if (i < KC) {
-        if (i == p) {
-          v = valid_p ? vg.sill : 1.0;
-        } else if (valid_p && i < nn) {
-          double dx = nbX[i] - xp, dy = nbY[i] - yp;
-          double d2 = fma(dy, dy, dx * dx);
-          if (DIM == 3) {
-            double dz = nbZ[i] - zp;
-            d2 = fma(dz, dz, d2);
-          }
-          v = gsk_cov<VK>(vg, d2);
+      if (i == p) {
+        v = valid_p ? vg.sill : 1.0;
+      } else if (i > p && i < nn) {
+        const double dx = nbX[i] - xp, dy = nbY[i] - yp;
+        double d2 = fma(dy, dy, dx * dx);
+        if (DIM == 3) {
+          const double dz = nbZ[i] - zp;
+          d2 = fma(dz, dz, d2);
         }
-      } else if (valid_p) {
-        const int r = i - KC;
-        if (r == 0) v = B[p];
-        else if (r == 1) v = V[p];
-        else if (r < e) {
-          if (a.es.kind == GSK_EST_ORDINARY) v = 1.0;
-          else {
-            const int *ex = a.es.exps[r - 2];
-            v = gsk_ipow(xp, ex[0]) * gsk_ipow(yp, ex[1]);
-            if (DIM == 3) v *= gsk_ipow(zp, ex[2]);
-          }
-        }
+        v = cov_fast<VK>(vg, d2);
       }
       col[i] = v;
     }
   }
   __syncwarp();
 
-  // ---- phase 4: blocked in-place Cholesky of the augmented matrix ----
+  // ---- phase 4: blocked in-place Cholesky of the augmented matrix (panels unrolled, static offsets) ----
   double acc[R][W];
-  for (int c0 = 0; c0 < KC; c0 += W) {
-    const int rmin = c0 / G;
+  double *Sl = S + l;  // element (i = r·G + l, column j) sits at Sl[col_off(j) − s_j + r·G]
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int i = r * G + l;
-#pragma unroll
-      for (int jj = 0; jj < W; ++jj) {
-        const int j = c0 + jj;
-        const int sj = col_start_row(j);
-        acc[r][jj] = (r >= rmin && i >= sj && i < RT) ? S[colOff[j] - sj + i] : 0.0;
-      }
-    }
-    // left-looking update from the finished columns p < c0
-    for (int p = 0; p < c0; ++p) {
-      const double *col = S + colOff[p] - col_start_row(p);
-      double piv[W];
-#pragma unroll
-      for (int jj = 0; jj < W; jj += 2) {
-        double2 t2 = *reinterpret_cast<const double2 *>(col + c0 + jj);
-        piv[jj] = t2.x;
-        piv[jj + 1] = t2.y;
-      }
+  for (int c0 = 0; c0 < KCMAX; c0 += W) {
+    if (c0 < KC) {
+      const int rmin = c0 / G;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int i = r * G + l;
         if (r >= rmin) {
-          const double own = (i < RT) ? col[i] : 0.0;
 #pragma unroll
-          for (int jj = 0; jj < W; ++jj) acc[r][jj] = fma(-own, piv[jj], acc[r][jj]);
+          for (int jj = 0; jj < W; ++jj) {
+            const int j = c0 + jj;
+            const int sj = j & ~(A - 1);
+            const bool in = ((r * G >= sj) || (r * G + l >= sj)) && GSK_ROW_OK(r);
+            acc[r][jj] = in ? Sl[col_off<RT, A>(j) - sj + r * G] : 0.0;
+          }
         }
       }
-    }
-    // the W×W panel
-#pragma unroll
-    for (int jj = 0; jj < W; ++jj) {
-      const int j = c0 + jj;
-      const int sj = col_start_row(j);
-      double *colj = S + colOff[j] - sj;
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (r >= rmin && r * G + l == j) PIV[0] = acc[r][jj];
-      __syncwarp();
-      const double rinv = rsqrt(PIV[0]);
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int i = r * G + l;
-        if (r >= rmin) {
-          acc[r][jj] *= rinv;
-          if (i >= j && i < RT) colj[i] = acc[r][jj];
-        }
-      }
-      __syncwarp();
-#pragma unroll
-      for (int j2 = jj + 1; j2 < W; ++j2) {
-        const double lj = colj[c0 + j2];
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-          if (r >= rmin) acc[r][j2] = fma(-acc[r][jj], lj, acc[r][j2]);
-      }
-    }
-  }
-
-  // ---- phase 5: Schur complement of the extra rows: Gm = Y Yᵀ ----
-  {
-    const int rmin = KC / G;
-    for (int cc = 0; cc < EP; cc += W) {
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int jj = 0; jj < W; ++jj) acc[r][jj] = 0.0;
-      for (int p = 0; p < KC; ++p) {
-        const double *col = S + colOff[p] - col_start_row(p);
+      // left-looking update from the finished columns p < c0
+      auto update = [&](int p) {
+        const double *col = S + col_off<RT, A>(p) - (p & ~(A - 1));
         double piv[W];
 #pragma unroll
         for (int jj = 0; jj < W; jj += 2) {
-          double2 t2 = *reinterpret_cast<const double2 *>(col + KC + cc + jj);
+          const double2 t2 = *reinterpret_cast<const double2 *>(col + c0 + jj);
           piv[jj] = t2.x;
           piv[jj + 1] = t2.y;
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const int i = r * G + l;
           if (r >= rmin) {
-            const double own = (i >= KC && i < RT) ? col[i] : 0.0;
+            const double own = GSK_ROW_OK(r) ? col[r * G + l] : 0.0;
 #pragma unroll
-            for (int jj = 0; jj < W; ++jj) acc[r][jj] = fma(own, piv[jj], acc[r][jj]);
+            for (int jj = 0; jj < W; ++jj) acc[r][jj] = fma(-own, piv[jj], acc[r][jj]);
           }
         }
+      };
+      if (UNROLL_P) {
+#pragma unroll
+        for (int p = 0; p < c0; ++p) update(p);
+      } else {
+#pragma unroll 2
+        for (int p = 0; p < c0; ++p) update(p);
+      }
+      // the W×W panel: pivots and row entries are exchanged by shuffles inside the group
+#pragma unroll
+      for (int jj = 0; jj < W; ++jj) {
+        const int j = c0 + jj;
+        const int sj = j & ~(A - 1);
+        const int ro = j / G, lo = j % G;  // owner of row j
+        const double d = __shfl_sync(0xffffffffu, acc[ro][jj], gbase + lo);
+        const double rinv = gsk_rsqrt(d);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (r >= rmin) {
+            acc[r][jj] *= rinv;
+            if ((r * G >= j || r * G + l >= j) && GSK_ROW_OK(r)) Sl[col_off<RT, A>(j) - sj + r * G] = acc[r][jj];
+          }
+        }
+#pragma unroll
+        for (int j2 = jj + 1; j2 < W; ++j2) {
+          const int r2 = (c0 + j2) / G, l2 = (c0 + j2) % G;  // owner of row c0 + j2
+          const double lj = __shfl_sync(0xffffffffu, acc[r2][jj], gbase + l2);
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (r >= rmin) acc[r][j2] = fma(-acc[r][jj], lj, acc[r][j2]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- phase 5: Schur complement of the extra rows: Gm = Y Yᵀ ----
+  for (int cc = 0; cc < EPr; cc += W) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int jj = 0; jj < W; ++jj) acc[r][jj] = 0.0;
+#pragma unroll 2
+    for (int p = 0; p < KC; ++p) {
+      const double *col = S + col_off<RT, A>(p) - (p & ~(A - 1));
+      double piv[W];
+#pragma unroll
+      for (int jj = 0; jj < W; jj += 2) {
+        const double2 t2 = *reinterpret_cast<const double2 *>(col + KC + cc + jj);
+        piv[jj] = t2.x;
+        piv[jj + 1] = t2.y;
       }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int i = r * G + l;
-        if (r >= rmin && i >= KC && i < RT) {
+        if (r * G + G > KC && r * G < KC + EPr) {  // slot holds extra rows (warp-uniform)
+          const double own = GSK_ROW_OK(r) ? col[r * G + l] : 0.0;
 #pragma unroll
-          for (int jj = 0; jj < W; ++jj) GM[(i - KC) * EP + cc + jj] = acc[r][jj];
+          for (int jj = 0; jj < W; ++jj) acc[r][jj] = fma(own, piv[jj], acc[r][jj]);
         }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = r * G + l;
+      if (i >= KC && i < KC + EPr) {
+#pragma unroll
+        for (int jj = 0; jj < W; ++jj) GM[(i - KC) * EPr + cc + jj] = acc[r][jj];
       }
     }
   }
@@ -310,19 +354,22 @@ __global__ void __launch_bounds__(CTA_THREADS) local_solve_kernel(const GskLocal
       if (c == 0) {
         mean = a.es.sk_mean + gbz;
         var = vg.sill - gbb;
+      } else if (c == 1) {
+        const double gff = GM[2 * EPr + 2], gfb = GM[2 * EPr], gfz = GM[2 * EPr + 1];
+        const double f0 = 1.0;  // OK, or UK of degree 0
+        const double nu = (gfb - f0) / gff;
+        mean = gbz - gfz * nu;
+        var = vg.sill - (gbb - gfb * nu + f0 * nu);
       } else {
         // solve Gff ν = gfb − f0 (c×c SPD) by Cholesky in place on GM
         double f0[GSK_MAX_DRIFT_TERMS], nu[GSK_MAX_DRIFT_TERMS];
         for (int t2 = 0; t2 < c; ++t2) {
-          if (a.es.kind == GSK_EST_ORDINARY) f0[t2] = 1.0;
-          else {
-            const int *ex = a.es.exps[t2];
-            double m = gsk_ipow(tc[0], ex[0]) * gsk_ipow(tc[1], ex[1]);
-            if (DIM == 3) m *= gsk_ipow(tc[2], ex[2]);
-            f0[t2] = m;
-          }
+          const int *ex = a.es.exps[t2];
+          double m = gsk_ipow(tc[0], ex[0]) * gsk_ipow(tc[1], ex[1]);
+          if (DIM == 3) m *= gsk_ipow(tc[2], ex[2]);
+          f0[t2] = m;
         }
-#define GFF(i, j) GM[(2 + (i)) * EP + 2 + (j)]
+#define GFF(i, j) GM[(2 + (i)) * EPr + 2 + (j)]
         for (int j = 0; j < c; ++j) {
           double d = GFF(j, j);
           for (int p = 0; p < j; ++p) d -= GFF(j, p) * GFF(j, p);
@@ -335,7 +382,7 @@ __global__ void __launch_bounds__(CTA_THREADS) local_solve_kernel(const GskLocal
           }
         }
         for (int j = 0; j < c; ++j) {
-          double s = GM[(2 + j) * EP + 0] - f0[j];
+          double s = GM[(2 + j) * EPr + 0] - f0[j];
           for (int p = 0; p < j; ++p) s -= GFF(j, p) * nu[p];
           nu[j] = s / GFF(j, j);
         }
@@ -347,8 +394,8 @@ __global__ void __launch_bounds__(CTA_THREADS) local_solve_kernel(const GskLocal
 #undef GFF
         double mz = 0.0, mb = 0.0, mf = 0.0;
         for (int j = 0; j < c; ++j) {
-          mz += GM[(2 + j) * EP + 1] * nu[j];
-          mb += GM[(2 + j) * EP + 0] * nu[j];
+          mz += GM[(2 + j) * EPr + 1] * nu[j];
+          mb += GM[(2 + j) * EPr + 0] * nu[j];
           mf += f0[j] * nu[j];
         }
         mean = gbz - mz;
@@ -360,17 +407,18 @@ __global__ void __launch_bounds__(CTA_THREADS) local_solve_kernel(const GskLocal
     a.mean[t] = mean;
     a.var[t] = var;
   }
+#undef GSK_ROW_OK
 }
 
-template <int G, int R, int W, int DIM, int VK>
+template <int G, int R, int W, int RS, int NT, int DIM, int VK>
 inline cudaError_t launch_one(const GskLocalArgs &a, int e, cudaStream_t st) {
+  constexpr int CTA_THREADS = NT;
   constexpr int TPW = 32 / G;
   constexpr int TPC = TPW * (CTA_THREADS / 32);
-  Layout L = make_layout<DIM>(a.k, e, W);
+  Layout L = make_layout<G, R, W, RS, DIM>(a.k, e);
   int nsup_pad = (3 * a.nsup + 3) & ~3;
-  int coff_pad = ((L.KC + 1) / 2 + 3) & ~3;
-  size_t smem = sizeof(double) * ((size_t)nsup_pad + coff_pad + (size_t)TPC * L.gsz);
-  auto kern = local_solve_kernel<G, R, W, DIM, VK>;
+  size_t smem = sizeof(double) * ((size_t)nsup_pad + (size_t)TPC * L.gsz);
+  auto kern = local_solve_kernel<G, R, W, RS, NT, DIM, VK>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   unsigned grid = (unsigned)((a.count + TPC - 1) / TPC);
@@ -378,24 +426,24 @@ inline cudaError_t launch_one(const GskLocalArgs &a, int e, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-template <int G, int R, int W>
+template <int G, int R, int W, int RS, int NT>
 inline cudaError_t launch_cfg(const GskLocalArgs &a, int e, cudaStream_t st) {
   const bool d3 = a.tg.dim == 3;
   switch (a.vg.kind) {
     case GSK_VARIO_GAUSSIAN:
-      return d3 ? launch_one<G, R, W, 3, GSK_VARIO_GAUSSIAN>(a, e, st) : launch_one<G, R, W, 2, GSK_VARIO_GAUSSIAN>(a, e, st);
+      return d3 ? launch_one<G, R, W, RS, NT, 3, GSK_VARIO_GAUSSIAN>(a, e, st) : launch_one<G, R, W, RS, NT, 2, GSK_VARIO_GAUSSIAN>(a, e, st);
     case GSK_VARIO_SPHERICAL:
-      return d3 ? launch_one<G, R, W, 3, GSK_VARIO_SPHERICAL>(a, e, st) : launch_one<G, R, W, 2, GSK_VARIO_SPHERICAL>(a, e, st);
+      return d3 ? launch_one<G, R, W, RS, NT, 3, GSK_VARIO_SPHERICAL>(a, e, st) : launch_one<G, R, W, RS, NT, 2, GSK_VARIO_SPHERICAL>(a, e, st);
     default:
-      return d3 ? launch_one<G, R, W, 3, GSK_VARIO_EXPONENTIAL>(a, e, st) : launch_one<G, R, W, 2, GSK_VARIO_EXPONENTIAL>(a, e, st);
+      return d3 ? launch_one<G, R, W, RS, NT, 3, GSK_VARIO_EXPONENTIAL>(a, e, st) : launch_one<G, R, W, RS, NT, 2, GSK_VARIO_EXPONENTIAL>(a, e, st);
   }
 }
 
 }  // namespace gsk_local
 
 // one translation unit per register/lanes configuration (compiled in parallel)
-cudaError_t gsk_local_launch_A(const GskLocalArgs &a, int e, cudaStream_t st);  // G=4  R=3 W=4  (≤ 12 rows)
-cudaError_t gsk_local_launch_B(const GskLocalArgs &a, int e, cudaStream_t st);  // G=4  R=6 W=4  (≤ 24 rows)
-cudaError_t gsk_local_launch_C(const GskLocalArgs &a, int e, cudaStream_t st);  // G=8  R=5 W=8  (≤ 40 rows)
-cudaError_t gsk_local_launch_D(const GskLocalArgs &a, int e, cudaStream_t st);  // G=16 R=5 W=8  (≤ 80 rows)
-cudaError_t gsk_local_launch_E(const GskLocalArgs &a, int e, cudaStream_t st);  // G=32 R=4 W=8  (≤ 128 rows)
+cudaError_t gsk_local_launch_A(const GskLocalArgs &a, int e, cudaStream_t st);  // G=4  R=3 W=4  12 rows, 128 thr
+cudaError_t gsk_local_launch_B(const GskLocalArgs &a, int e, cudaStream_t st);  // G=4  R=6 W=4  24 rows, 128 thr
+cudaError_t gsk_local_launch_C(const GskLocalArgs &a, int e, cudaStream_t st);  // G=8  R=5 W=8  40 rows, 128 thr
+cudaError_t gsk_local_launch_D(const GskLocalArgs &a, int e, cudaStream_t st);  // G=16 R=5 W=8  72 rows,  64 thr
+cudaError_t gsk_local_launch_E(const GskLocalArgs &a, int e, cudaStream_t st);  // G=32 R=4 W=8 112 rows, 128 thr
