@@ -231,6 +231,8 @@ extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) {
   v.range = p->vario_range;
   v.inv_r = 1.0 / p->vario_range;
   v.inv_r2 = v.inv_r * v.inv_r;
+  v.hcs = 0.5 * v.cs;
+  v.m15cs = -1.5 * v.cs;
 
   // estimator
   GskEstimator &es = ctx->es;

@@ -26,6 +26,7 @@ struct GskVario {
   double range;   // r
   double inv_r2;  // 1/r²
   double inv_r;   // 1/r
+  double hcs, m15cs;  // 0.5·cs, −1.5·cs (spherical polynomial with cs folded in)
 };
 
 struct GskTargets {

@@ -76,17 +76,15 @@ __device__ __forceinline__ double gsk_rsqrt(double d) {
   return y;
 }
 
-// sqrt(u) for u > 0 (u == 0 yields NaN, discarded by the callers' d2 > 0 select): coupled Goldschmidt
+// sqrt(u) for u > 0 (u == 0 yields NaN, discarded by the callers' d2 > 0 select)
 __device__ __forceinline__ double gsk_sqrt_pos(double u) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u));
-  double g = u * y, h = 0.5 * y;
-  double r = fma(-g, h, 0.5);
-  g = fma(g, r, g);
-  h = fma(h, r, h);
-  r = fma(-g, h, 0.5);
-  g = fma(g, r, g);
-  return g;
+  // one cubically convergent step: sqrt(u) = t(1 + e/2 + 3e²/8 + O(e³)), t = u·y, e = 1 − u·y²  (|e| <= 2^-21)
+  const double t = u * y;
+  const double e = fma(-t, y, 1.0);
+  const double q = e * fma(0.375, e, 0.5);
+  return fma(t, q, t);
 }
 
 // covariance from the squared distance, fast-path math (same formulas as gsk_cov)
@@ -98,8 +96,7 @@ __device__ __forceinline__ double cov_fast(const GskVario &v, double d2) {
   } else if (VK == GSK_VARIO_SPHERICAL) {
     const double u = d2 * v.inv_r2;
     const double t = gsk_sqrt_pos(u);
-    const double g = fma(t, fma(0.5, u, -1.5), 1.0);
-    c = (u < 1.0) ? v.cs * g : 0.0;
+    c = (u < 1.0) ? fma(t, fma(v.hcs, u, v.m15cs), v.cs) : 0.0;  // cs(1 − 1.5t + 0.5t³)
   } else {
     c = v.cs * exp(-3.0 * v.inv_r * gsk_sqrt_pos(d2));
   }
@@ -169,69 +166,104 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
   const bool estimate = live && nn >= a.min_neighbors && nn > 0;
   if (!estimate) nn = 0;
 
-  // ---- phase 1+2: gather neighbours; block-support RHS b_j = mean_q C(‖t + δ_q − x_j‖); extra rows ----
+  // ---- phase 1+2: gather my neighbours (j = l, l+G, …) into registers; block-support RHS
+  //      b_j = mean_q C(‖t + δ_q − x_j‖) with the q loop outermost so that the JM evaluations of a
+  //      lane are independent (ILP); write the extra rows of column j ----
+  constexpr int JM = (KCMAX + G - 1) / G;
   {
-    const double inv_q = 1.0 / (double)a.nsup;
-    const int nextra = RT - KC;
-    for (int j = l; j < KC; j += G) {
-      const bool valid = j < nn;
+    double nx[JM], ny[JM], nz[JM], nv[JM], bacc[JM];
+#pragma unroll
+    for (int jj = 0; jj < JM; ++jj) {
+      const int j = jj * G + l;
       double4 rc = make_double4(0.0, 0.0, 0.0, 0.0);
-      if (valid) rc = a.rec_orig[a.nbr[t * a.k + j]];
-      nbX[j] = rc.x;
-      nbY[j] = rc.y;
-      if (DIM == 3) nbZ[j] = rc.z;
-      double acc = 0.0;
-      if (valid) {
-        for (int q = 0; q < a.nsup; ++q) {
-          const double dx = (tc[0] + sup[q]) - rc.x;
-          const double dy = (tc[1] + sup[a.nsup + q]) - rc.y;
+      if (j < nn) rc = a.rec_orig[a.nbr[t * a.k + j]];
+      nx[jj] = rc.x; ny[jj] = rc.y; nz[jj] = rc.z; nv[jj] = rc.w;
+      bacc[jj] = 0.0;
+      if (j < KC) {
+        nbX[j] = rc.x;
+        nbY[j] = rc.y;
+        if (DIM == 3) nbZ[j] = rc.z;
+      }
+    }
+    for (int q = 0; q < a.nsup; ++q) {
+      const double ux = tc[0] + sup[q], uy = tc[1] + sup[a.nsup + q];
+      const double uz = (DIM == 3) ? tc[2] + sup[2 * a.nsup + q] : 0.0;
+#pragma unroll
+      for (int jj = 0; jj < JM; ++jj) {
+        if (jj * G < nn) {  // warp-uniform-ish guard (whole slot empty)
+          const double dx = ux - nx[jj], dy = uy - ny[jj];
           double d2 = fma(dy, dy, dx * dx);
           if (DIM == 3) {
-            const double dz = (tc[2] + sup[2 * a.nsup + q]) - rc.z;
+            const double dz = uz - nz[jj];
             d2 = fma(dz, dz, d2);
           }
-          acc += cov_fast<VK>(vg, d2);
+          bacc[jj] += cov_fast<VK>(vg, d2);
         }
       }
-      double *colj = S + col_off<RT, A>(j) - (j & ~(A - 1));
-      colj[KC] = acc * inv_q;
-      colj[KC + 1] = valid ? ((a.es.kind == GSK_EST_SIMPLE) ? rc.w - a.es.sk_mean : rc.w) : 0.0;
-      for (int r2 = 2; r2 < nextra; ++r2) {
-        double v = 0.0;
-        if (valid && r2 < e) {
-          if (a.es.kind == GSK_EST_ORDINARY) v = 1.0;
-          else {
-            const int *ex = a.es.exps[r2 - 2];
-            v = gsk_ipow(rc.x, ex[0]) * gsk_ipow(rc.y, ex[1]);
-            if (DIM == 3) v *= gsk_ipow(rc.z, ex[2]);
+    }
+    const double inv_q = 1.0 / (double)a.nsup;
+    const int nextra = RT - KC;
+#pragma unroll
+    for (int jj = 0; jj < JM; ++jj) {
+      const int j = jj * G + l;
+      if (j < KC) {
+        const bool valid = j < nn;
+        double *colj = S + col_off<RT, A>(j) - (j & ~(A - 1));
+        colj[KC] = valid ? bacc[jj] * inv_q : 0.0;
+        colj[KC + 1] = valid ? ((a.es.kind == GSK_EST_SIMPLE) ? nv[jj] - a.es.sk_mean : nv[jj]) : 0.0;
+        for (int r2 = 2; r2 < nextra; ++r2) {
+          double v = 0.0;
+          if (valid && r2 < e) {
+            if (a.es.kind == GSK_EST_ORDINARY) v = 1.0;
+            else {
+              const int *ex = a.es.exps[r2 - 2];
+              v = gsk_ipow(nx[jj], ex[0]) * gsk_ipow(ny[jj], ex[1]);
+              if (DIM == 3) v *= gsk_ipow(nz[jj], ex[2]);
+            }
           }
+          colj[KC + r2] = v;
         }
-        colj[KC + r2] = v;
       }
     }
   }
   __syncwarp();
 
-  // ---- phase 3: covariance block in place (column p, neighbour rows >= p & ~(A−1)) ----
-  for (int p = 0; p < KC; ++p) {
-    const bool valid_p = p < nn;
-    const double xp = nbX[p], yp = nbY[p], zp = (DIM == 3) ? nbZ[p] : 0.0;
-    const int sp = p & ~(A - 1);
-    double *col = S + col_off<RT, A>(p) - sp;
-    for (int i = sp + l; i < KC; i += G) {
-      double v = 0.0;
-      if (i == p) {
-        v = valid_p ? vg.sill : 1.0;
-      } else if (i > p && i < nn) {
-        const double dx = nbX[i] - xp, dy = nbY[i] - yp;
-        double d2 = fma(dy, dy, dx * dx);
-        if (DIM == 3) {
-          const double dz = nbZ[i] - zp;
-          d2 = fma(dz, dz, d2);
+  // ---- phase 3: covariance block in place. Lane l owns rows i = r·G + l (coordinates in registers) and
+  //      walks the columns p; the R evaluations per column are independent ----
+  {
+    constexpr int RS_S = (KCMAX + G - 1) / G;  // slots that can hold neighbour rows
+    double xi[RS_S], yi[RS_S], zi[RS_S];
+#pragma unroll
+    for (int r = 0; r < RS_S; ++r) {
+      const int i = r * G + l;
+      const bool ok = i < KC;
+      xi[r] = ok ? nbX[i] : 0.0;
+      yi[r] = ok ? nbY[i] : 0.0;
+      zi[r] = (DIM == 3 && ok) ? nbZ[i] : 0.0;
+    }
+    for (int p = 0; p < KC; ++p) {
+      const bool valid_p = p < nn;
+      const double xp = nbX[p], yp = nbY[p], zp = (DIM == 3) ? nbZ[p] : 0.0;
+      const int sp = p & ~(A - 1);
+      double *col = S + col_off<RT, A>(p) - sp + l;
+#pragma unroll
+      for (int r = 0; r < RS_S; ++r) {
+        if (r * G + G > sp && r * G < KC) {  // slot intersects rows [sp, KC): warp-uniform
+          const int i = r * G + l;
+          double v = 0.0;
+          if (i > p && i < nn) {
+            const double dx = xi[r] - xp, dy = yi[r] - yp;
+            double d2 = fma(dy, dy, dx * dx);
+            if (DIM == 3) {
+              const double dz = zi[r] - zp;
+              d2 = fma(dz, dz, d2);
+            }
+            v = cov_fast<VK>(vg, d2);
+          }
+          if (i == p) v = valid_p ? vg.sill : 1.0;
+          if (i >= sp && i < KC) col[r * G] = v;
         }
-        v = cov_fast<VK>(vg, d2);
       }
-      col[i] = v;
     }
   }
   __syncwarp();
@@ -309,37 +341,31 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
     }
   }
 
-  // ---- phase 5: Schur complement of the extra rows: Gm = Y Yᵀ ----
+  // ---- phase 5: Schur complement of the extra rows: Gm = Y Yᵀ (only the slots that hold extra rows work) ----
   for (int cc = 0; cc < EPr; cc += W) {
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int jj = 0; jj < W; ++jj) acc[r][jj] = 0.0;
-#pragma unroll 2
-    for (int p = 0; p < KC; ++p) {
-      const double *col = S + col_off<RT, A>(p) - (p & ~(A - 1));
-      double piv[W];
-#pragma unroll
-      for (int jj = 0; jj < W; jj += 2) {
-        const double2 t2 = *reinterpret_cast<const double2 *>(col + KC + cc + jj);
-        piv[jj] = t2.x;
-        piv[jj + 1] = t2.y;
-      }
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (r * G + G > KC && r * G < KC + EPr) {  // slot holds extra rows (warp-uniform)
-          const double own = GSK_ROW_OK(r) ? col[r * G + l] : 0.0;
-#pragma unroll
-          for (int jj = 0; jj < W; ++jj) acc[r][jj] = fma(own, piv[jj], acc[r][jj]);
-        }
-      }
-    }
-#pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int i = r * G + l;
-      if (i >= KC && i < KC + EPr) {
+      if (r * G + G > KC && r * G < KC + EPr) {  // slot holds extra rows (warp-uniform)
+        double g[W];
 #pragma unroll
-        for (int jj = 0; jj < W; ++jj) GM[(i - KC) * EPr + cc + jj] = acc[r][jj];
+        for (int jj = 0; jj < W; ++jj) g[jj] = 0.0;
+        const int i = r * G + l;
+        const bool mine = i >= KC && i < KC + EPr;
+#pragma unroll 4
+        for (int p = 0; p < KC; ++p) {
+          const double *col = S + col_off<RT, A>(p) - (p & ~(A - 1));
+          const double own = mine ? col[i] : 0.0;
+#pragma unroll
+          for (int jj = 0; jj < W; jj += 2) {
+            const double2 t2 = *reinterpret_cast<const double2 *>(col + KC + cc + jj);
+            g[jj] = fma(own, t2.x, g[jj]);
+            g[jj + 1] = fma(own, t2.y, g[jj + 1]);
+          }
+        }
+        if (mine) {
+#pragma unroll
+          for (int jj = 0; jj < W; ++jj) GM[(i - KC) * EPr + cc + jj] = g[jj];
+        }
       }
     }
   }
