@@ -1,0 +1,150 @@
+# GSKrige.jl — Julia shim that keeps `solve(problem, KrigingSolver(...))` drop-in while the per-location
+# loops run in libgskrige.so (B200, sm_100a). It mirrors the host logic of the reference
+# (GeoStatsSolvers.jl v0.7.16, src/estimation/krig.jl:76-164, src/ui.jl:11-50, src/utils.jl:5-15) and
+# replaces exactly two functions — exactsolve (krig.jl:166-186) and approxsolve (krig.jl:188-234) — by a
+# single `ccall` each. NOTE: Julia is not installed in the build or GPU images of this repository, so this
+# file is NOT executed by the test-suite; geostatssolvers.jl_b200/host.py is the same logic in Python and
+# is what the tests exercise. julia/verify_semantics.jl prints the third-party behaviours (SURVEY V1-V9)
+# a maintainer with a Julia install should confirm.
+module GSKrige
+
+using GeoStatsBase, GeoStatsModels, Variography, Meshes, GeoTables, Tables, Unitful, Distances
+import GeoStatsBase: solve, preprocess
+
+const LIB = get(ENV, "GSKRIGE_LIB", joinpath(@__DIR__, "..", "geostatssolvers.jl_b200", "csrc", "libgskrige.so"))
+
+# ---- struct gsk_problem (include/gskrige.h), field for field -----------------------------------------
+struct GskProblem
+  abi_version::Int32
+  dim::Int32
+  n_samples::Int64
+  coords::NTuple{3,Ptr{Float64}}
+  values::Ptr{Float64}
+  grid_dims::NTuple{3,Int64}
+  grid_origin::NTuple{3,Float64}
+  grid_spacing::NTuple{3,Float64}
+  n_points::Int64
+  point_coords::NTuple{3,Ptr{Float64}}
+  target_first::Int64
+  target_count::Int64
+  n_support::Int32
+  support_offsets::NTuple{3,Ptr{Float64}}
+  vario_kind::Int32
+  vario_range::Float64
+  vario_sill::Float64
+  vario_nugget::Float64
+  gaussian_nugget_eps::Float64
+  estimator::Int32
+  sk_mean::Float64
+  uk_degree::Int32
+  min_neighbors::Int32
+  max_neighbors::Int32
+  ball_radius::Float64
+  flags::UInt32
+end
+
+mutable struct Context
+  handle::Ptr{Cvoid}
+  function Context(device::Integer=0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:gsk_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Cint), h, device)
+    rc == 0 || error("libgskrige: ", unsafe_string(ccall((:gsk_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    ctx = new(h[])
+    finalizer(c -> ccall((:gsk_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.handle), ctx)
+  end
+end
+
+const DEFAULT = Ref{Union{Nothing,Context}}(nothing)
+context() = (DEFAULT[] === nothing && (DEFAULT[] = Context(0)); DEFAULT[])
+
+check(ctx, rc) = rc == 0 ? nothing :
+  (msg = unsafe_string(ccall((:gsk_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.handle));
+   rc == -2 ? throw(ArgumentError("unsupported by the B200 Kriging path (no CPU fallback): $msg")) : error("libgskrige ($rc): $msg"))
+
+# ---- what crosses the ABI ------------------------------------------------------------------------------
+variokind(::GaussianVariogram) = Int32(0)
+variokind(::SphericalVariogram) = Int32(1)
+variokind(::ExponentialVariogram) = Int32(2)
+variokind(γ) = throw(ArgumentError("variogram $(typeof(γ)) is not supported by the B200 Kriging path"))
+
+function support_offsets(pdomain::CartesianGrid, γ)
+  dim = embeddim(pdomain)
+  sp = collect(Float64, ustrip.(spacing(pdomain)))
+  bufs = [zeros(125) for _ in 1:3]
+  n = ccall((:gsk_default_support, LIB), Cint, (Cint, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+            dim, sp, ustrip(range(γ)), bufs[1], bufs[2], bufs[3], 125)
+  n > 0 || error("gsk_default_support failed")
+  [b[1:n] for b in bufs[1:dim]]
+end
+support_offsets(pdomain, γ) = [zeros(1) for _ in 1:embeddim(pdomain)]  # PointSet targets: point support
+
+"one ccall: replaces exactsolve / approxsolve (krig.jl:166-234)"
+function krige(samples, pdomain, var, estimator, searcher, minneighbors, islocal::Bool; ctx=context())
+  γ = estimator.γ
+  sdom = domain(samples)
+  dim = embeddim(sdom)
+  n = nelements(sdom)
+  X = [Float64[ustrip(coordinates(centroid(sdom, i))[d]) for i in 1:n] for d in 1:dim]       # SoA
+  z = collect(Float64, ustrip.(getproperty(samples, var)))
+  sup = support_offsets(pdomain, γ)
+  T = nelements(pdomain)
+  isgrid = pdomain isa CartesianGrid
+  P = isgrid ? [Float64[] for _ in 1:dim] : [Float64[ustrip(coordinates(centroid(pdomain, i))[d]) for i in 1:T] for d in 1:dim]
+  tup(v, fill) = ntuple(d -> d <= length(v) ? v[d] : fill, 3)
+  ptrs(v) = ntuple(d -> d <= length(v) ? pointer(v[d]) : Ptr{Float64}(C_NULL), 3)
+  est, skmean, deg = estimator isa GeoStatsModels.SimpleKriging ? (Int32(0), Float64(ustrip(estimator.μ)), Int32(0)) :
+                     estimator isa GeoStatsModels.UniversalKriging ? (Int32(2), 0.0, Int32(maximum(estimator.exponents))) :
+                     estimator isa GeoStatsModels.OrdinaryKriging ? (Int32(1), 0.0, Int32(0)) :
+                     throw(ArgumentError("ExternalDriftKriging (`drifts`) is not supported by the B200 Kriging path"))
+  k = islocal ? Int32(maxneighbors(searcher)) : Int32(0)            # the CLAMPED k (ui.jl:16-23)
+  radius = (islocal && searcher isa KBallSearch) ? Float64(ustrip(Meshes.radius(searcher.ball))) : NaN
+  μ = Vector{Float64}(undef, T); σ² = Vector{Float64}(undef, T); nn = Vector{Int32}(undef, T)
+  GC.@preserve X z sup P μ σ² nn begin
+    prob = GskProblem(1, dim, n, ptrs(X), pointer(z),
+      isgrid ? tup(collect(Int64, size(pdomain)), 1) : (0, 1, 1),
+      isgrid ? tup(collect(Float64, ustrip.(coordinates(minimum(pdomain)))), 0.0) : (0.0, 0.0, 0.0),
+      isgrid ? tup(collect(Float64, ustrip.(spacing(pdomain))), 1.0) : (1.0, 1.0, 1.0),
+      isgrid ? 0 : T, ptrs(P), 0, -1, length(sup[1]), ptrs(sup),
+      variokind(γ), ustrip(range(γ)), ustrip(sill(γ)), ustrip(nugget(γ)), 1e-6,
+      est, skmean, deg, Int32(minneighbors), k, radius, UInt32(3))
+    check(ctx, ccall((:gsk_krige, LIB), Cint,
+      (Ptr{Cvoid}, Ref{GskProblem}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+      ctx.handle, prob, μ, σ², nn, C_NULL))
+  end
+  if islocal && any(<(max(minneighbors, 1)), nn)                    # krig.jl:213-214 → (missing, missing)
+    miss = nn .< max(minneighbors, 1)
+    return ifelse.(miss, missing, μ), ifelse.(miss, missing, σ²)
+  end
+  μ, σ²
+end
+
+# ---- the reference's host logic, unchanged in behaviour (krig.jl:76-164) -------------------------------
+elunit(x) = typeunit(eltype(x))
+typeunit(::Type) = NoUnits
+typeunit(::Type{Q}) where {Q<:Quantity} = unit(Q)
+uadjust(x) = uadjust(elunit(x), x)
+uadjust(::Unitful.Units, x) = x
+uadjust(U::Unitful.AffineUnits, x) = uconvert.(absoluteunit(U), x)
+
+"drop-in for GeoStatsSolvers.solve(problem, ::KrigingSolver); `solver` is the reference's own solver object"
+function solve_b200(problem::EstimationProblem, solver; ctx=context())
+  pdata = data(problem); dtable = values(pdata); ddomain = domain(pdata); pdomain = domain(problem)
+  μs = []; σs = []
+  for covars in covariables(problem, solver), var in covars.names
+    p = covars.params[Set([var])]
+    p.distance isa Euclidean || throw(ArgumentError("non-Euclidean `distance` is not supported by the B200 Kriging path"))
+    z = uadjust(Tables.getcolumn(Tables.columns(dtable), var))                     # krig.jl:94
+    inds = findall(!ismissing, z)                                                  # krig.jl:97
+    isempty(inds) && throw(AssertionError("all samples of $var are missing, aborting..."))   # krig.jl:100-102
+    samples = georef((; var => collect(skipmissing(z))), view(ddomain, inds))      # krig.jl:105-107
+    estimator = GeoStatsSolvers.kriging_ui(pdomain, p.variogram, p.mean, p.degree, p.drifts)        # ui.jl:40-50
+    searcher = GeoStatsSolvers.searcher_ui(domain(samples), p.maxneighbors, p.distance, p.neighborhood)  # ui.jl:11-32 (warns + clamps)
+    varμ, varσ = krige(samples, pdomain, var, estimator, searcher, p.minneighbors, !isnothing(p.maxneighbors); ctx)  # krig.jl:151-157
+    u = elunit(z)
+    push!(μs, var => (u == NoUnits ? varμ : varμ .* u))
+    push!(σs, Symbol(var, "_variance") => (u == NoUnits ? varσ : varσ .* u^2))      # krig.jl:160
+  end
+  georef((; μs..., σs...), pdomain)                                                # krig.jl:163
+end
+
+end # module
