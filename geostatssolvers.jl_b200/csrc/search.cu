@@ -174,8 +174,12 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
   const double slack = 1e-9 * bn.cell_max;
 
   int ob0[3] = {1, 1, 1}, ob1[3] = {0, 0, 0};  // previously scanned block (empty)
-  int mg[3] = {a.margin0[0], a.margin0[1], a.margin0[2]};
+  // The block grows one bin per level from the tile's own bins out to the density-based margin
+  // (centre-out order keeps the top-k insertions short: near samples arrive first), and by ×1.5
+  // per level after that. The stop test only runs once the density-based margin is reached.
+  int mg[3] = {0, 0, 0};
   bool have_old = false;
+  bool reached = a.margin0[0] == 0 && a.margin0[1] == 0 && a.margin0[2] == 0;
 
   for (;;) {
     int nb0[3], nb1[3];
@@ -279,13 +283,21 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
       double safe2 = (margin > 0.0) ? margin * margin : 0.0;
       done = (cnt == K && worst < safe2) || (safe2 > r2);
     }
-    if (whole || __syncthreads_and(done ? 1 : 0)) break;
+    if (whole) break;
+    if (reached && __syncthreads_and(done ? 1 : 0)) break;
+    bool next_reached = true;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       ob0[d] = nb0[d];
       ob1[d] = nb1[d];
-      mg[d] += max(1, mg[d] / 2);
+      if (!reached) {
+        if (mg[d] < a.margin0[d]) ++mg[d];
+        next_reached = next_reached && mg[d] >= a.margin0[d];
+      } else {
+        mg[d] += max(1, mg[d] / 2);
+      }
     }
+    reached = reached || next_reached;
     have_old = true;
   }
 
