@@ -87,18 +87,49 @@ __device__ __forceinline__ double gsk_sqrt_pos(double u) {
   return fma(t, q, t);
 }
 
+// exp(x) for x <= 0, branch-free (so that independent evaluations interleave): x = n·ln2 + f, |f| <= ln2/2,
+// degree-12 Taylor/Horner on f (truncation 2e-17 relative), scaled by 2^n through the exponent field.
+// Arguments below −700 are clamped (result ~1e-304, i.e. 0 at double precision for a covariance).
+__device__ __forceinline__ double gsk_exp_neg(double x) {
+  x = fmax(x, -700.0);
+  const double t = fma(x, 1.4426950408889634, 6755399441055744.0);  // round(x·log2 e) in the low mantissa bits
+  const int n = __double2loint(t);
+  const double nd = t - 6755399441055744.0;
+  double f = fma(nd, -6.93147180369123816490e-01, x);
+  f = fma(nd, -1.90821492927058770002e-10, f);
+  double p = 2.08767569878680989792e-09;           // 1/12!
+  p = fma(p, f, 2.50521083854417187751e-08);       // 1/11!
+  p = fma(p, f, 2.75573192239858906526e-07);       // 1/10!
+  p = fma(p, f, 2.75573192239858906526e-06);       // 1/9!
+  p = fma(p, f, 2.48015873015873015873e-05);       // 1/8!
+  p = fma(p, f, 1.98412698412698412698e-04);       // 1/7!
+  p = fma(p, f, 1.38888888888888888889e-03);       // 1/6!
+  p = fma(p, f, 8.33333333333333333333e-03);       // 1/5!
+  p = fma(p, f, 4.16666666666666666667e-02);       // 1/4!
+  p = fma(p, f, 1.66666666666666666667e-01);       // 1/3!
+  p = fma(p, f, 0.5);
+  p = fma(p, f, 1.0);
+  p = fma(p, f, 1.0);
+  // scale by 2^n, n in [-1010, 0]: two steps keep the intermediate normal
+  const int n1 = n >> 1, n2 = n - n1;
+  const double s1 = __hiloint2double((1023 + n1) << 20, 0);
+  const double s2 = __hiloint2double((1023 + n2) << 20, 0);
+  return (p * s1) * s2;
+}
+
 // covariance from the squared distance, fast-path math (same formulas as gsk_cov)
 template <int VK>
 __device__ __forceinline__ double cov_fast(const GskVario &v, double d2) {
   double c;
   if (VK == GSK_VARIO_GAUSSIAN) {
-    c = v.cs * exp(-3.0 * d2 * v.inv_r2);
+    c = v.cs * gsk_exp_neg(-3.0 * d2 * v.inv_r2);
   } else if (VK == GSK_VARIO_SPHERICAL) {
     const double u = d2 * v.inv_r2;
     const double t = gsk_sqrt_pos(u);
     c = (u < 1.0) ? fma(t, fma(v.hcs, u, v.m15cs), v.cs) : 0.0;  // cs(1 − 1.5t + 0.5t³)
   } else {
-    c = v.cs * exp(-3.0 * v.inv_r * gsk_sqrt_pos(d2));
+    const double h = (d2 > 0.0) ? gsk_sqrt_pos(d2) : 0.0;
+    c = v.cs * gsk_exp_neg(-3.0 * v.inv_r * h);
   }
   return (d2 > 0.0) ? c : v.sill;
 }
@@ -189,16 +220,14 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
       const double ux = tc[0] + sup[q], uy = tc[1] + sup[a.nsup + q];
       const double uz = (DIM == 3) ? tc[2] + sup[2 * a.nsup + q] : 0.0;
 #pragma unroll
-      for (int jj = 0; jj < JM; ++jj) {
-        if (jj * G < nn) {  // warp-uniform-ish guard (whole slot empty)
-          const double dx = ux - nx[jj], dy = uy - ny[jj];
-          double d2 = fma(dy, dy, dx * dx);
-          if (DIM == 3) {
-            const double dz = uz - nz[jj];
-            d2 = fma(dz, dz, d2);
-          }
-          bacc[jj] += cov_fast<VK>(vg, d2);
+      for (int jj = 0; jj < JM; ++jj) {  // branch-free: the JM chains interleave (invalid lanes compute on zeros)
+        const double dx = ux - nx[jj], dy = uy - ny[jj];
+        double d2 = fma(dy, dy, dx * dx);
+        if (DIM == 3) {
+          const double dz = uz - nz[jj];
+          d2 = fma(dz, dz, d2);
         }
+        bacc[jj] += cov_fast<VK>(vg, d2);
       }
     }
     const double inv_q = 1.0 / (double)a.nsup;
@@ -241,27 +270,32 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
       yi[r] = ok ? nbY[i] : 0.0;
       zi[r] = (DIM == 3 && ok) ? nbZ[i] : 0.0;
     }
-    for (int p = 0; p < KC; ++p) {
-      const bool valid_p = p < nn;
-      const double xp = nbX[p], yp = nbY[p], zp = (DIM == 3) ? nbZ[p] : 0.0;
-      const int sp = p & ~(A - 1);
-      double *col = S + col_off<RT, A>(p) - sp + l;
+    // columns in blocks of A share their first stored row sb, hence the set of active slots (static)
 #pragma unroll
-      for (int r = 0; r < RS_S; ++r) {
-        if (r * G + G > sp && r * G < KC) {  // slot intersects rows [sp, KC): warp-uniform
-          const int i = r * G + l;
-          double v = 0.0;
-          if (i > p && i < nn) {
-            const double dx = xi[r] - xp, dy = yi[r] - yp;
-            double d2 = fma(dy, dy, dx * dx);
-            if (DIM == 3) {
-              const double dz = zi[r] - zp;
-              d2 = fma(dz, dz, d2);
+    for (int sb = 0; sb < KCMAX; sb += A) {
+      if (sb < KC) {
+        const int rlo = sb / G;
+        for (int pp = 0; pp < A; ++pp) {
+          const int p = sb + pp;
+          const bool valid_p = p < nn;
+          const double xp = nbX[p], yp = nbY[p], zp = (DIM == 3) ? nbZ[p] : 0.0;
+          double *col = S + col_off<RT, A>(sb) + pp * (RT - sb) - sb + l;
+#pragma unroll
+          for (int r = 0; r < RS_S; ++r) {
+            if (r >= rlo) {  // static after unrolling
+              const int i = r * G + l;
+              const double dx = xi[r] - xp, dy = yi[r] - yp;
+              double d2 = fma(dy, dy, dx * dx);
+              if (DIM == 3) {
+                const double dz = zi[r] - zp;
+                d2 = fma(dz, dz, d2);
+              }
+              double v = cov_fast<VK>(vg, d2);
+              v = (i > p && i < nn) ? v : 0.0;
+              v = (i == p) ? (valid_p ? vg.sill : 1.0) : v;
+              if (i >= sb && i < KC) col[r * G] = v;
             }
-            v = cov_fast<VK>(vg, d2);
           }
-          if (i == p) v = valid_p ? vg.sill : 1.0;
-          if (i >= sp && i < KC) col[r * G] = v;
         }
       }
     }
