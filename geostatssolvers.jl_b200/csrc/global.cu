@@ -297,38 +297,125 @@ __global__ void rhs_kernel(GArgs g, GskTargets tg, const double *__restrict__ su
   Bm[i + (long long)t * g.np] = v;
 }
 
-// ---- the hot kernel: Y tile = Linv[mt, 0..mt]·B[0..mt, nt]; epilogue reduces Y² and Y·Y_E per target ----
-// partial[(mt·(1+ne) + s)·nbpad + t]
-__global__ void __launch_bounds__(256) ygemm_kernel(const double *__restrict__ X, long long ld,
-                                                    const double *__restrict__ Bm, const double *__restrict__ YE,
-                                                    int ne, long long nbpad, double *__restrict__ partial) {
-  __shared__ double As[BK][NB + 1];
-  __shared__ double Bs[BK][NB + 1];
-  __shared__ double red[16][NB + 1];
+// ---- the hot kernel (K5): Y tile = Linv[mt, 0..mt]·B[0..mt, nt] on the FP64 tensor path ------------------
+// 128×128 output tile per CTA, K stepped by 16 through a 3-stage cp.async pipeline, 8 warps each owning a
+// 64×32 sub-tile computed with mma.sync.m16n8k16 f64 (SASS DMMA; tcgen05 has no FP64 kind). The epilogue
+// never stores Y: per target column it reduces Σ y² and Σ y·Y_E[:,s] over the tile's 128 rows and writes
+// 1+ne partial sums:  partial[(mt·(1+ne) + s)·nbpad + t].
+constexpr int GT = 128;          // tile edge
+constexpr int GKS = 16;          // k per pipeline stage
+constexpr int GSTAGES = 3;
+constexpr int AS_LD = GT + 4;    // A stage: [k][m], m contiguous; ≡ 4 (mod 16) doubles → conflict-free fragment loads
+constexpr int BS_LD = GKS + 4;   // B stage: [n][k], k contiguous
+constexpr int A_STAGE = GKS * AS_LD, B_STAGE = GT * BS_LD;
+constexpr size_t YGEMM_SMEM = sizeof(double) * (size_t)GSTAGES * (A_STAGE + B_STAGE);
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+}
+
+__global__ void __launch_bounds__(256, 1) ygemm_dmma_kernel(const double *__restrict__ X, long long ld,
+                                                            const double *__restrict__ Bm,
+                                                            const double *__restrict__ YE, int ne, long long nbpad,
+                                                            double *__restrict__ partial) {
+  extern __shared__ __align__(16) double gsm[];
+  double *As = gsm;                                  // [GSTAGES][GKS][AS_LD]
+  double *Bs = gsm + (size_t)GSTAGES * A_STAGE;      // [GSTAGES][GT][BS_LD]
+  __shared__ double red[2][GT];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, t = lane & 3;
   const int nt = blockIdx.x, mt = gridDim.y - 1 - blockIdx.y;  // longest row tiles first
-  const long long i0 = (long long)mt * NB, t0 = (long long)nt * NB;
-  double acc[4][4] = {};
-  tile_mma<false>(X + i0, ld, Bm + t0 * ld, ld, (mt + 1) * NB, acc, As, Bs);
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int tm = tx * 4, tn = ty * 4;
+  const long long i0 = (long long)mt * GT, t0 = (long long)nt * GT;
+  const int nk = (mt + 1) * (GT / GKS);
+
+  auto load_stage = [&](int s, int kt) {
+    double *as = As + (size_t)s * A_STAGE;
+    double *bs = Bs + (size_t)s * B_STAGE;
+    const long long k0 = (long long)kt * GKS;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tid + 256 * i;
+      const int k = c >> 6, mc = c & 63;
+      cp_async16(as + k * AS_LD + 2 * mc, X + i0 + 2 * mc + (k0 + k) * ld);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = tid + 256 * i;
+      const int n = c >> 3, kc = c & 7;
+      cp_async16(bs + n * BS_LD + 2 * kc, Bm + (t0 + n) * ld + k0 + 2 * kc);
+    }
+  };
+
+  double acc[4][4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < GSTAGES - 1; ++s) {
+    if (s < nk) load_stage(s, s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(GSTAGES - 2) : "memory");
+    __syncthreads();
+    if (kt + GSTAGES - 1 < nk) load_stage((kt + GSTAGES - 1) % GSTAGES, kt + GSTAGES - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const double *as = As + (size_t)(kt % GSTAGES) * A_STAGE + wm * 64 + g;
+    const double *bs = Bs + (size_t)(kt % GSTAGES) * B_STAGE + (wn * 32 + g) * BS_LD + t;
+    double bf[4][4];
+#pragma unroll
+    for (int n8 = 0; n8 < 4; ++n8)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bf[n8][i] = bs[n8 * 8 * BS_LD + 4 * i];
+#pragma unroll
+    for (int m16 = 0; m16 < 4; ++m16) {
+      double af[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) af[i] = as[(t + 4 * (i >> 1)) * AS_LD + m16 * 16 + 8 * (i & 1)];
+#pragma unroll
+      for (int n8 = 0; n8 < 4; ++n8) {
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+            "{%12,%13,%14,%15}, {%0,%1,%2,%3};"
+            : "+d"(acc[m16][n8][0]), "+d"(acc[m16][n8][1]), "+d"(acc[m16][n8][2]), "+d"(acc[m16][n8][3])
+            : "d"(af[0]), "d"(af[1]), "d"(af[2]), "d"(af[3]), "d"(af[4]), "d"(af[5]), "d"(af[6]), "d"(af[7]),
+              "d"(bf[n8][0]), "d"(bf[n8][1]), "d"(bf[n8][2]), "d"(bf[n8][3]));
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+  // fused epilogue: c0,c1 → row g, cols 2t,2t+1; c2,c3 → row g+8 (of each 16×8 fragment)
   for (int s = 0; s <= ne; ++s) {
-    double w[4];
+    double w[4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) w[i] = (s == 0) ? 0.0 : YE[i0 + tm + i + (long long)(s - 1) * ld];
+    for (int m16 = 0; m16 < 4; ++m16)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      double v = 0.0;
+      for (int h = 0; h < 2; ++h)
+        w[m16][h] = (s == 0) ? 0.0 : YE[i0 + wm * 64 + m16 * 16 + g + 8 * h + (long long)(s - 1) * ld];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v = fma(acc[i][j], (s == 0) ? acc[i][j] : w[i], v);
-      red[tx][tn + j] = v;
+    for (int n8 = 0; n8 < 4; ++n8) {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        double v = 0.0;
+#pragma unroll
+        for (int m16 = 0; m16 < 4; ++m16) {
+          const double y0 = acc[m16][n8][cc], y1 = acc[m16][n8][cc + 2];
+          v = fma(y0, (s == 0) ? y0 : w[m16][0], v);
+          v = fma(y1, (s == 0) ? y1 : w[m16][1], v);
+        }
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (g == 0) red[wm][wn * 32 + n8 * 8 + 2 * t + cc] = v;
+      }
     }
     __syncthreads();
-    if (threadIdx.x < NB) {
-      double v = 0.0;
-#pragma unroll
-      for (int r = 0; r < 16; ++r) v += red[r][threadIdx.x];
-      partial[((long long)mt * (1 + ne) + s) * nbpad + t0 + threadIdx.x] = v;
-    }
+    if (tid < GT) partial[((long long)mt * (1 + ne) + s) * nbpad + t0 + tid] = red[0][tid] + red[1][tid];
     __syncthreads();
   }
 }
@@ -441,7 +528,7 @@ int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const doub
   GlobalPlan *g = new GlobalPlan();
   ctx->gplan = g;
   g->n = n;
-  g->np = (n + NB - 1) / NB * NB;
+  g->np = (n + GT - 1) / GT * GT;  // multiple of the GEMM tile (and of the factorisation block)
   g->ne = 1 + ctx->es.nterms;
   const long long np = g->np;
   const int nblk = (int)(np / NB);
@@ -496,10 +583,11 @@ int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const doub
 
   // batch of targets per GEMM: bound B to ~2 GB
   long long batch = (long long)((2.0e9 / 8.0) / (double)np);
-  batch = std::max<long long>(NB, std::min<long long>(batch, 32768) / NB * NB);
+  batch = std::max<long long>(GT, std::min<long long>(batch, 32768) / GT * GT);
   g->batch = batch;
   GSK_CUDA_CHECK(ctx, cudaMalloc(&g->Bm, sizeof(double) * (size_t)np * batch));
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->partial, sizeof(double) * (size_t)nblk * (1 + g->ne) * batch));
+  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->partial, sizeof(double) * (size_t)(np / GT) * (1 + g->ne) * batch));
+  GSK_CUDA_CHECK(ctx, cudaFuncSetAttribute(ygemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)YGEMM_SMEM));
   GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
   return GSK_OK;
 }
@@ -514,7 +602,7 @@ int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, double *d
   GArgs ga{ctx->d_rec_orig, g->n, np, ctx->vg, ctx->prob.dim};
   for (long long off = 0; off < count; off += g->batch) {
     const int nb = (int)std::min<long long>(g->batch, count - off);
-    const int nbp = (nb + NB - 1) / NB * NB;
+    const int nbp = (nb + GT - 1) / GT * GT;
     if (nbp > nb)  // zero the padded target columns so the GEMM reads defined data
       GSK_CUDA_CHECK(ctx, cudaMemsetAsync(g->Bm + (size_t)nb * np, 0, sizeof(double) * (size_t)(nbp - nb) * np, st));
     dim3 grid((unsigned)((np + 255) / 256), (unsigned)nb);
@@ -529,9 +617,9 @@ int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, double *d
         rhs_kernel<GSK_VARIO_EXPONENTIAL><<<grid, 256, 0, st>>>(ga, ctx->tg, ctx->d_sup, ctx->prob.n_support, first + off, nb, g->Bm);
         break;
     }
-    ygemm_kernel<<<dim3((unsigned)(nbp / NB), (unsigned)nblk), 256, 0, st>>>(g->X, np, g->Bm, g->YE, g->ne, g->batch,
-                                                                            g->partial);
-    global_epilogue_kernel<<<(nb + 127) / 128, 128, 0, st>>>(g->partial, nblk, g->ne, g->batch, nb, g->GEE, ctx->es,
+    ygemm_dmma_kernel<<<dim3((unsigned)(nbp / GT), (unsigned)(np / GT)), 256, YGEMM_SMEM, st>>>(
+        g->X, np, g->Bm, g->YE, g->ne, g->batch, g->partial);
+    global_epilogue_kernel<<<(nb + 127) / 128, 128, 0, st>>>(g->partial, (int)(np / GT), g->ne, g->batch, nb, g->GEE, ctx->es,
                                                              ctx->tg, ctx->vg.sill, ctx->prob.flags, first + off,
                                                              d_mean + off, d_var + off);
     if (launches) *launches += 3;

@@ -178,15 +178,28 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
   double tc[3] = {0.0, 0.0, 0.0};
   int nn = 0;
   if (live) {
-    long long lin = a.first + t;
+    const long long lin = a.first + t;
     if (a.tg.is_grid) {
-      long long rem = lin;
+      if (a.tg.gdim[0] * a.tg.gdim[1] * a.tg.gdim[2] < 0x7fffffffLL) {  // 32-bit index math (the common case)
+        unsigned rem = (unsigned)lin;
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        if (d < a.tg.dim) {
-          long long c = rem % a.tg.gdim[d];
-          rem /= a.tg.gdim[d];
-          tc[d] = gsk_cell_center(a.tg.gorg[d], a.tg.gsp[d], c);
+        for (int d = 0; d < 3; ++d) {
+          if (d < a.tg.dim) {
+            const unsigned gd = (unsigned)a.tg.gdim[d];
+            const unsigned qd = rem / gd;
+            tc[d] = gsk_cell_center(a.tg.gorg[d], a.tg.gsp[d], (long long)(rem - qd * gd));
+            rem = qd;
+          }
+        }
+      } else {
+        long long rem = lin;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          if (d < a.tg.dim) {
+            long long c = rem % a.tg.gdim[d];
+            rem /= a.tg.gdim[d];
+            tc[d] = gsk_cell_center(a.tg.gorg[d], a.tg.gsp[d], c);
+          }
         }
       }
     } else {
@@ -207,7 +220,8 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
     for (int jj = 0; jj < JM; ++jj) {
       const int j = jj * G + l;
       double4 rc = make_double4(0.0, 0.0, 0.0, 0.0);
-      if (j < nn) rc = a.rec_orig[a.nbr[t * a.k + j]];
+      const int idx = (live && j < a.k) ? a.nbr[t * a.k + j] : -1;  // −1 padded beyond nn: no dependence on the nn load
+      if (idx >= 0) rc = a.rec_orig[idx];
       nx[jj] = rc.x; ny[jj] = rc.y; nz[jj] = rc.z; nv[jj] = rc.w;
       bacc[jj] = 0.0;
       if (j < KC) {
