@@ -6,6 +6,7 @@
 #include <math.h>
 
 #include <cmath>
+#include <cstdlib>
 
 #include <algorithm>
 
@@ -127,7 +128,10 @@ int gsk_build_bins(gsk_ctx *ctx, const double *hx, const double *hy, const doubl
     hi[d] = mx;
   }
   // cells sized for ~occ samples each (k/4…k/2 per cell, capped)
-  double occ = std::min(8.0, std::max(2.0, k / 6.0));
+  // tunables (development): GSK_BIN_OCC_DIV (samples per cell = k / div), GSK_MARGIN_FACTOR
+  static const double occ_div = getenv("GSK_BIN_OCC_DIV") ? atof(getenv("GSK_BIN_OCC_DIV")) : 24.0;
+  static const double margin_factor = getenv("GSK_MARGIN_FACTOR") ? atof(getenv("GSK_MARGIN_FACTOR")) : 1.0;
+  double occ = std::min(8.0, std::max(1.0, k / occ_div));
   int live = 0;
   double vol = 1.0;
   for (int d = 0; d < dim; ++d)
@@ -164,7 +168,7 @@ int gsk_build_bins(gsk_ctx *ctx, const double *hx, const double *hy, const doubl
     double cd = (live <= 1) ? 2.0 : (live == 2 ? M_PI : 4.0 * M_PI / 3.0);
     double r0 = (live > 0) ? pow((double)k / (dens * cd), 1.0 / live) : 0.0;
     for (int d = 0; d < 3; ++d) {
-      int m = (d < dim && hi[d] > lo[d]) ? (int)ceil(1.15 * r0 / b.cell[d]) : 0;
+      int m = (d < dim && hi[d] > lo[d]) ? (int)ceil(margin_factor * r0 / b.cell[d]) : 0;
       ctx->margin0[d] = std::max(m, (d < dim) ? 1 : 0);
     }
   }

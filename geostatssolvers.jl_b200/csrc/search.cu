@@ -81,7 +81,7 @@ __device__ __forceinline__ int block_excl_scan(int v, int *warp_buf, int *total)
   return base + incl - v;
 }
 
-template <int TX, int TY, int TZ>
+template <int TX, int TY, int TZ, int DIM>
 __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
   static_assert(TX * TY * TZ == NT, "tile must hold NT targets");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -236,10 +236,14 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
             const double4 rc = stage[s];
             double dx = tc[0] - rc.x;
             double d2 = __dmul_rn(dx, dx);
-            double dy = tc[1] - rc.y;
-            d2 = __dadd_rn(d2, __dmul_rn(dy, dy));
-            double dz = tc[2] - rc.z;
-            d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
+            if (DIM > 1) {
+              double dy = tc[1] - rc.y;
+              d2 = __dadd_rn(d2, __dmul_rn(dy, dy));
+            }
+            if (DIM > 2) {
+              double dz = tc[2] - rc.z;
+              d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
+            }
             if (d2 > worst) continue;
             const int oi = (int)__double_as_longlong(rc.w);
             if (d2 == worst && oi > worst_i) continue;
@@ -362,14 +366,14 @@ int gsk_launch_search(gsk_ctx *ctx, long long first, long long count, int *d_nn,
   }
   cudaError_t e;
   if (dim == 1) {
-    e = cudaFuncSetAttribute(search_kernel<NT, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) search_kernel<NT, 1, 1><<<nblocks, NT, smem, ctx->stream>>>(a);
+    e = cudaFuncSetAttribute(search_kernel<NT, 1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) search_kernel<NT, 1, 1, 1><<<nblocks, NT, smem, ctx->stream>>>(a);
   } else if (dim == 2) {
-    e = cudaFuncSetAttribute(search_kernel<16, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) search_kernel<16, 8, 1><<<nblocks, NT, smem, ctx->stream>>>(a);
+    e = cudaFuncSetAttribute(search_kernel<16, 8, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) search_kernel<16, 8, 1, 2><<<nblocks, NT, smem, ctx->stream>>>(a);
   } else {
-    e = cudaFuncSetAttribute(search_kernel<8, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) search_kernel<8, 4, 4><<<nblocks, NT, smem, ctx->stream>>>(a);
+    e = cudaFuncSetAttribute(search_kernel<8, 4, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) search_kernel<8, 4, 4, 3><<<nblocks, NT, smem, ctx->stream>>>(a);
   }
   GSK_CUDA_CHECK(ctx, e);
   GSK_CUDA_CHECK(ctx, cudaGetLastError());

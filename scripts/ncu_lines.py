@@ -17,8 +17,11 @@ for r in rows:
         except ValueError:
             continue
         d = dict(zip(hdr[4:], r[4:]))
-        inst = int(d.get("Instructions Executed", "0") or 0)
-        samp = int(d.get("# Samples", "0") or 0)
+        def _i(x):
+            try: return int(x)
+            except (TypeError, ValueError): return 0
+        inst = _i(d.get("Instructions Executed"))
+        samp = _i(d.get("# Samples"))
         a = agg.setdefault(key, [0, 0, r[1][:90]])
         a[0] += inst; a[1] += samp
 tot_i = sum(a[0] for a in agg.values()); tot_s = sum(a[1] for a in agg.values())
