@@ -1,5 +1,7 @@
 // local_solve.cu — picks the lanes/registers configuration of K3 for (k, extra rows) and launches it.
-#include "local_solve.cuh"
+#include <stdlib.h>
+
+#include "local_solve_small.cuh"
 
 int gsk_launch_local_solve(gsk_ctx *ctx, long long first, long long count, const int *d_nn, const int *d_nbr,
                            double *d_mean, double *d_var, int *launches) {
@@ -25,7 +27,10 @@ int gsk_launch_local_solve(gsk_ctx *ctx, long long first, long long count, const
   const int e = 2 + ctx->es.nterms;
   auto rows = [&](int W) { return (a.k + W - 1) / W * W + (e + W - 1) / W * W; };
   cudaError_t err;
-  if (rows(4) <= 12) err = gsk_local_launch_A(a, e, ctx->stream);
+  static const bool no_small = getenv("GSK_NO_SMALL_KERNEL") != nullptr;  // development switch
+  if (!no_small && a.k <= gsk_local::SK_KMAX && (ctx->es.kind == GSK_EST_SIMPLE || ctx->es.nterms == 1))
+    err = gsk_local_launch_small(a, ctx->stream);
+  else if (rows(4) <= 12) err = gsk_local_launch_A(a, e, ctx->stream);
   else if (rows(4) <= 24) err = gsk_local_launch_B(a, e, ctx->stream);
   else if (rows(8) <= 40) err = gsk_local_launch_C(a, e, ctx->stream);
   else if (rows(8) <= 72) err = gsk_local_launch_D(a, e, ctx->stream);

@@ -1,0 +1,257 @@
+// local_solve_small.cuh — K3 specialised for k <= 20 neighbours with Simple / Ordinary Kriging (e <= 3
+// extra rows): the configuration BASELINE.json's metric is quoted on (C2: k = 20, OK). Same
+// formulation as local_solve.cuh (augmented in-place Cholesky + Schur/Gram algebra), but
+//   * 4 lanes per target, 5 register slots of neighbour rows, panels of 4 columns, all loops unrolled:
+//     every shared-memory address is base + immediate and every register index is static;
+//   * the extra rows (b, z, ones) never touch shared memory: lane l keeps extra row l in registers
+//     (yreg[20]); they are updated alongside the neighbour rows and their Gram products are formed with
+//     shuffles — shared memory per target is just the packed factor (244 doubles = 1952 B), so three
+//     128-thread CTAs (96 targets) fit per SM instead of two;
+//   * pivot column coordinates, pivots and panel rows all travel by warp shuffles inside the 4-lane group.
+#pragma once
+#include "local_solve.cuh"
+
+namespace gsk_local {
+
+constexpr int SK_KMAX = 20;   // neighbour columns (multiple of 4)
+constexpr int SK_R = SK_KMAX / 4;
+constexpr int SK_STOR = col_off<SK_KMAX, 4>(SK_KMAX);  // packed factor, rows >= p & ~3 of column p
+constexpr int SK_GSZ = ((SK_STOR + 15) / 16) * 16 + 4;  // ≡ 4 (mod 16) doubles: groups spread over the banks
+
+template <int DIM, int VK>
+__global__ void __launch_bounds__(128, 3) local_solve_small_kernel(const GskLocalArgs a, const int KC) {
+  constexpr int G = 4, R = SK_R, W = 4, RT = SK_KMAX, A = 4, KM = SK_KMAX;
+  constexpr int TPC = 32;  // targets per CTA
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sm = reinterpret_cast<double *>(smem_raw);
+  double *sup = sm;
+  const int nsup_pad = (3 * a.nsup + 3) & ~3;
+  const int tid = threadIdx.x, lane = tid & 31, l = lane & 3, grp = tid >> 2, gbase = lane & ~3;
+  for (int i = tid; i < 3 * a.nsup; i += 128) sup[i] = a.sup[i];
+  __syncthreads();
+  double *S = sm + nsup_pad + (size_t)grp * SK_GSZ;
+  double *Sl = S + l;
+
+  const long long t = (long long)blockIdx.x * TPC + grp;
+  const bool live = t < a.count;
+  const GskVario vg = a.vg;
+
+  // ---- target centroid ----
+  double tc[3] = {0.0, 0.0, 0.0};
+  int nn = 0;
+  if (live) {
+    const long long lin = a.first + t;
+    if (a.tg.is_grid) {
+      if (a.tg.gdim[0] * a.tg.gdim[1] * a.tg.gdim[2] < 0x7fffffffLL) {
+        unsigned rem = (unsigned)lin;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          if (d < a.tg.dim) {
+            const unsigned gd = (unsigned)a.tg.gdim[d];
+            const unsigned qd = rem / gd;
+            tc[d] = gsk_cell_center(a.tg.gorg[d], a.tg.gsp[d], (long long)(rem - qd * gd));
+            rem = qd;
+          }
+        }
+      } else {
+        long long rem = lin;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          if (d < a.tg.dim) {
+            long long c = rem % a.tg.gdim[d];
+            rem /= a.tg.gdim[d];
+            tc[d] = gsk_cell_center(a.tg.gorg[d], a.tg.gsp[d], c);
+          }
+        }
+      }
+    } else {
+      for (int d = 0; d < a.tg.dim; ++d) tc[d] = a.tg.pts[d][lin];
+    }
+    nn = a.nn[t];
+  }
+  const bool estimate = live && nn >= a.min_neighbors && nn > 0;
+  if (!estimate) nn = 0;
+
+  // ---- phase 1: gather my neighbours j = 4·jj + l ----
+  double nx[R], ny[R], nz[R], nv[R], bacc[R];
+#pragma unroll
+  for (int jj = 0; jj < R; ++jj) {
+    const int j = jj * G + l;
+    double4 rc = make_double4(0.0, 0.0, 0.0, 0.0);
+    const int idx = (live && j < a.k) ? a.nbr[t * a.k + j] : -1;
+    if (idx >= 0) rc = a.rec_orig[idx];
+    nx[jj] = rc.x; ny[jj] = rc.y; nz[jj] = rc.z;
+    nv[jj] = (a.es.kind == GSK_EST_SIMPLE) ? rc.w - a.es.sk_mean : rc.w;
+    bacc[jj] = 0.0;
+  }
+  // ---- phase 2: block-support RHS, q outermost (5 independent chains per lane) ----
+  for (int q = 0; q < a.nsup; ++q) {
+    const double ux = tc[0] + sup[q], uy = tc[1] + sup[a.nsup + q];
+    const double uz = (DIM == 3) ? tc[2] + sup[2 * a.nsup + q] : 0.0;
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      const double dx = ux - nx[jj], dy = uy - ny[jj];
+      double d2 = fma(dy, dy, dx * dx);
+      if (DIM == 3) {
+        const double dz = uz - nz[jj];
+        d2 = fma(dz, dz, d2);
+      }
+      bacc[jj] += cov_fast<VK>(vg, d2);
+    }
+  }
+  // ---- phase 3: extra rows into registers: lane 0 ← b, lane 1 ← z, lane 2 ← ones (OK), lane 3 ← 0 ----
+  double yreg[KM];
+  {
+    const double inv_q = 1.0 / (double)a.nsup;
+    const bool ok_row = a.es.kind != GSK_EST_SIMPLE;
+#pragma unroll
+    for (int p = 0; p < KM; ++p) {
+      const double vb = __shfl_sync(0xffffffffu, bacc[p / G], gbase + (p % G)) * inv_q;
+      const double vz = __shfl_sync(0xffffffffu, nv[p / G], gbase + (p % G));
+      const bool valid_p = p < nn;
+      double v = (l == 0) ? vb : ((l == 1) ? vz : ((l == 2 && ok_row) ? 1.0 : 0.0));
+      yreg[p] = valid_p ? v : 0.0;
+    }
+  }
+  // ---- phase 4: covariance block into shared memory, column p rows >= p & ~3 (all static) ----
+#pragma unroll
+  for (int p = 0; p < KM; ++p) {
+    if (p < KC) {
+      const int sb = p & ~3, rlo = sb / G;
+      const double xp = __shfl_sync(0xffffffffu, nx[p / G], gbase + (p % G));
+      const double yp = __shfl_sync(0xffffffffu, ny[p / G], gbase + (p % G));
+      const double zp = (DIM == 3) ? __shfl_sync(0xffffffffu, nz[p / G], gbase + (p % G)) : 0.0;
+      const bool valid_p = p < nn;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (r >= rlo) {
+          const int i = r * G + l;
+          const double dx = nx[r] - xp, dy = ny[r] - yp;
+          double d2 = fma(dy, dy, dx * dx);
+          if (DIM == 3) {
+            const double dz = nz[r] - zp;
+            d2 = fma(dz, dz, d2);
+          }
+          double v = cov_fast<VK>(vg, d2);
+          v = (i > p && i < nn) ? v : 0.0;
+          v = (i == p) ? (valid_p ? vg.sill : 1.0) : v;
+          Sl[col_off<RT, A>(p) - sb + r * G] = v;
+        }
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- phase 5: blocked in-place Cholesky; extra rows ride along in registers ----
+  double acc[R][W], accx[W];
+#pragma unroll
+  for (int c0 = 0; c0 < KM; c0 += W) {
+    if (c0 < KC) {
+      const int rmin = c0 / G;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (r >= rmin)
+#pragma unroll
+          for (int jj = 0; jj < W; ++jj) acc[r][jj] = Sl[col_off<RT, A>(c0 + jj) - c0 + r * G];
+#pragma unroll
+      for (int jj = 0; jj < W; ++jj) accx[jj] = yreg[c0 + jj];
+      // left-looking update from the finished columns
+#pragma unroll
+      for (int p = 0; p < c0; ++p) {
+        const double *col = S + col_off<RT, A>(p) - (p & ~3);
+        const double2 t01 = *reinterpret_cast<const double2 *>(col + c0);
+        const double2 t23 = *reinterpret_cast<const double2 *>(col + c0 + 2);
+        const double piv[W] = {t01.x, t01.y, t23.x, t23.y};
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (r >= rmin) {
+            const double own = col[r * G + l];
+#pragma unroll
+            for (int jj = 0; jj < W; ++jj) acc[r][jj] = fma(-own, piv[jj], acc[r][jj]);
+          }
+        }
+#pragma unroll
+        for (int jj = 0; jj < W; ++jj) accx[jj] = fma(-yreg[p], piv[jj], accx[jj]);
+      }
+      // the 4×4 panel
+#pragma unroll
+      for (int jj = 0; jj < W; ++jj) {
+        const int j = c0 + jj;
+        const double d = __shfl_sync(0xffffffffu, acc[j / G][jj], gbase + (j % G));
+        const double rinv = gsk_rsqrt(d);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (r >= rmin) {
+            acc[r][jj] *= rinv;
+            if (r * G >= j || r * G + l >= j) Sl[col_off<RT, A>(j) - c0 + r * G] = acc[r][jj];
+          }
+        }
+        accx[jj] *= rinv;
+        yreg[j] = accx[jj];
+#pragma unroll
+        for (int j2 = jj + 1; j2 < W; ++j2) {
+          const double lj = __shfl_sync(0xffffffffu, acc[(c0 + j2) / G][jj], gbase + ((c0 + j2) % G));
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (r >= rmin) acc[r][j2] = fma(-acc[r][jj], lj, acc[r][j2]);
+          accx[j2] = fma(-accx[jj], lj, accx[j2]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- phase 6: Gram products of the extra rows by shuffles. Lane l forms <row l, row l> and
+  //      <row l, row (l+1)%3>: lane 0 → bb, bz; lane 1 → zz, zf; lane 2 → ff, fb ----
+  double g_self = 0.0, g_next = 0.0;
+  {
+    const int src = gbase + ((l + 1) % 3);
+#pragma unroll
+    for (int p = 0; p < KM; ++p) {
+      const double o = __shfl_sync(0xffffffffu, yreg[p], src);
+      g_self = fma(yreg[p], yreg[p], g_self);
+      g_next = fma(yreg[p], o, g_next);
+    }
+  }
+  const double gbb = __shfl_sync(0xffffffffu, g_self, gbase + 0);
+  const double gbz = __shfl_sync(0xffffffffu, g_next, gbase + 0);
+  const double gzf = __shfl_sync(0xffffffffu, g_next, gbase + 1);
+  const double gff = __shfl_sync(0xffffffffu, g_self, gbase + 2);
+  const double gfb = __shfl_sync(0xffffffffu, g_next, gbase + 2);
+
+  if (l == 0 && live) {
+    double mean = NAN, var = NAN;
+    if (estimate) {
+      if (a.es.kind == GSK_EST_SIMPLE) {
+        mean = a.es.sk_mean + gbz;
+        var = vg.sill - gbb;
+      } else {
+        const double nu = (gfb - 1.0) / gff;
+        mean = gbz - gzf * nu;
+        var = vg.sill - (gbb - gfb * nu + nu);
+      }
+      if (a.flags & GSK_FLAG_CLAMP_VARIANCE) var = (var > 0.0 || var != var) ? var : 0.0;
+      if (a.flags & GSK_FLAG_SQRT_ROUNDTRIP) { double sd = sqrt(var); var = sd * sd; }
+    }
+    a.mean[t] = mean;
+    a.var[t] = var;
+  }
+}
+
+template <int DIM, int VK>
+inline cudaError_t launch_small_one(const GskLocalArgs &a, cudaStream_t st) {
+  const int KC = (a.k + 3) / 4 * 4;
+  const int nsup_pad = (3 * a.nsup + 3) & ~3;
+  const size_t smem = sizeof(double) * ((size_t)nsup_pad + 32 * (size_t)SK_GSZ);
+  auto kern = local_solve_small_kernel<DIM, VK>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return err;
+  const unsigned grid = (unsigned)((a.count + 31) / 32);
+  kern<<<grid, 128, smem, st>>>(a, KC);
+  return cudaGetLastError();
+}
+
+}  // namespace gsk_local
+
+// k <= 20, Simple / Ordinary Kriging (UK degree 0 is OK): the small-system fast path
+cudaError_t gsk_local_launch_small(const GskLocalArgs &a, cudaStream_t st);
