@@ -125,12 +125,45 @@ extern "C" GSK_API int gsk_create(gsk_ctx **out, int device_id) {
   return GSK_OK;
 }
 
+int gsk_buf(gsk_ctx *ctx, GskBufId id, size_t bytes, void **out) {
+  if (bytes == 0) bytes = 16;
+  if (ctx->bufcap[id] < bytes) {
+    cudaFree(ctx->bufp[id]);
+    ctx->bufp[id] = nullptr;
+    ctx->bufcap[id] = 0;
+    cudaError_t e = cudaMalloc(&ctx->bufp[id], bytes);
+    if (e != cudaSuccess) {
+      ctx->err = std::string("device allocation failed: ") + cudaGetErrorString(e);
+      return GSK_ERR_NOMEM;
+    }
+    ctx->bufcap[id] = bytes;
+  }
+  *out = ctx->bufp[id];
+  return GSK_OK;
+}
+
+int gsk_host_stage(gsk_ctx *ctx, size_t bytes, void **out) {
+  if (ctx->h_stage_cap < bytes) {
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr;
+    ctx->h_stage_cap = 0;
+    cudaError_t e = cudaHostAlloc(&ctx->h_stage, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+      ctx->err = std::string("pinned host allocation failed: ") + cudaGetErrorString(e);
+      return GSK_ERR_NOMEM;
+    }
+    ctx->h_stage_cap = bytes;
+  }
+  *out = ctx->h_stage;
+  return GSK_OK;
+}
+
 static void free_plan(gsk_ctx *ctx) {
-  cudaFree(ctx->d_rec_orig); ctx->d_rec_orig = nullptr;
-  cudaFree(ctx->d_rec_sorted); ctx->d_rec_sorted = nullptr;
-  cudaFree(ctx->d_cell_start); ctx->d_cell_start = nullptr;
-  cudaFree(ctx->d_sup); ctx->d_sup = nullptr;
-  for (int d = 0; d < 3; ++d) { cudaFree(ctx->d_pts[d]); ctx->d_pts[d] = nullptr; }
+  // device buffers stay cached in ctx->bufp; only the plan state is dropped
+  ctx->d_rec_orig = ctx->d_rec_sorted = nullptr;
+  ctx->d_cell_start = nullptr;
+  ctx->d_sup = nullptr;
+  for (int d = 0; d < 3; ++d) ctx->d_pts[d] = nullptr;
   gsk_global_free(ctx);
   ctx->planned = false;
 }
@@ -140,6 +173,8 @@ extern "C" GSK_API void gsk_destroy(gsk_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_plan(ctx);
+  for (int i = 0; i < BUF_COUNT; ++i) cudaFree(ctx->bufp[i]);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   cudaFree(ctx->d_nn);
   cudaFree(ctx->d_nbr);
   cudaFree(ctx->d_mean);
@@ -264,7 +299,8 @@ extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) {
   if (!tg.is_grid) {
     tg.npts = p->n_points;
     for (int d = 0; d < dim; ++d) {
-      GSK_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_pts[d], sizeof(double) * (size_t)std::max<int64_t>(1, p->n_points)));
+      rc = gsk_buf(ctx, (GskBufId)(BUF_PTS0 + d), sizeof(double) * (size_t)std::max<int64_t>(1, p->n_points), (void **)&ctx->d_pts[d]);
+      if (rc != GSK_OK) return rc;
       GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_pts[d], p->point_coords[d], sizeof(double) * (size_t)p->n_points,
                                           cudaMemcpyHostToDevice, ctx->stream));
       tg.pts[d] = ctx->d_pts[d];
@@ -277,7 +313,8 @@ extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) {
     for (int d = 0; d < dim; ++d)
       if (p->support_offsets[d])
         for (int q = 0; q < p->n_support; ++q) sup[(size_t)d * p->n_support + q] = p->support_offsets[d][q];
-    GSK_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_sup, sizeof(double) * sup.size()));
+    rc = gsk_buf(ctx, BUF_SUP, sizeof(double) * sup.size(), (void **)&ctx->d_sup);
+    if (rc != GSK_OK) return rc;
     GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_sup, sup.data(), sizeof(double) * sup.size(), cudaMemcpyHostToDevice,
                                         ctx->stream));
     GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -20,17 +20,14 @@ __device__ __forceinline__ int bin_of(double x, double lo, double inv, int nb) {
   return b;
 }
 
-__global__ void pack_and_count_kernel(const double *__restrict__ x, const double *__restrict__ y,
-                                      const double *__restrict__ z, const double *__restrict__ v, long long n,
-                                      GskBins bins, double4 *__restrict__ rec_orig, int *__restrict__ cell_of,
-                                      int *__restrict__ counts) {
+__global__ void count_kernel(const double4 *__restrict__ rec_orig, long long n, GskBins bins,
+                             int *__restrict__ cell_of, int *__restrict__ counts) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double px = x[i], py = y ? y[i] : 0.0, pz = z ? z[i] : 0.0;
-  rec_orig[i] = make_double4(px, py, pz, v[i]);
-  int bx = bin_of(px, bins.lo[0], bins.inv[0], bins.nb[0]);
-  int by = bin_of(py, bins.lo[1], bins.inv[1], bins.nb[1]);
-  int bz = bin_of(pz, bins.lo[2], bins.inv[2], bins.nb[2]);
+  const double4 r = rec_orig[i];
+  int bx = bin_of(r.x, bins.lo[0], bins.inv[0], bins.nb[0]);
+  int by = bin_of(r.y, bins.lo[1], bins.inv[1], bins.nb[1]);
+  int bz = bin_of(r.z, bins.lo[2], bins.inv[2], bins.nb[2]);
   int c = (bz * bins.nb[1] + by) * bins.nb[0] + bx;
   cell_of[i] = c;
   atomicAdd(&counts[c], 1);
@@ -173,43 +170,34 @@ int gsk_build_bins(gsk_ctx *ctx, const double *hx, const double *hy, const doubl
     }
   }
 
-  // ---- device buffers ----
+  // ---- device buffers (cached in the context) and one pinned-host staged upload of {x,y,z,value} ----
   cudaStream_t st = ctx->stream;
-  double *tmp = nullptr;
   int *cell_of = nullptr, *counts = nullptr;
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&tmp, sizeof(double) * 4 * (size_t)n));
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&cell_of, sizeof(int) * (size_t)n));
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&counts, sizeof(int) * (size_t)ncells * 2));
+  int rc;
+  if ((rc = gsk_buf(ctx, BUF_REC_ORIG, sizeof(double4) * (size_t)n, (void **)&ctx->d_rec_orig)) != GSK_OK) return rc;
+  if ((rc = gsk_buf(ctx, BUF_REC_SORTED, sizeof(double4) * (size_t)(n + 1), (void **)&ctx->d_rec_sorted)) != GSK_OK) return rc;
+  if ((rc = gsk_buf(ctx, BUF_CELL_START, sizeof(int) * (size_t)(ncells + 1), (void **)&ctx->d_cell_start)) != GSK_OK) return rc;
+  if ((rc = gsk_buf(ctx, BUF_CELL_OF, sizeof(int) * (size_t)n, (void **)&cell_of)) != GSK_OK) return rc;
+  if ((rc = gsk_buf(ctx, BUF_COUNTS, sizeof(int) * (size_t)ncells * 2, (void **)&counts)) != GSK_OK) return rc;
   int *cursor = counts + ncells;
-  cudaFree(ctx->d_rec_orig);
-  cudaFree(ctx->d_rec_sorted);
-  cudaFree(ctx->d_cell_start);
-  ctx->d_rec_orig = ctx->d_rec_sorted = nullptr;
-  ctx->d_cell_start = nullptr;
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_rec_orig, sizeof(double4) * (size_t)n));
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_rec_sorted, sizeof(double4) * (size_t)(n + 1)));
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_cell_start, sizeof(int) * (size_t)(ncells + 1)));
-  double *dx = tmp, *dy = tmp + n, *dz = tmp + 2 * n, *dv = tmp + 3 * n;
-  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(dx, hx, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-  if (dim > 1) GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(dy, hy, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-  if (dim > 2) GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(dz, hz, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(dv, hv, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  double4 *hrec = nullptr;
+  if ((rc = gsk_host_stage(ctx, sizeof(double4) * (size_t)n, (void **)&hrec)) != GSK_OK) return rc;
+  for (long long i = 0; i < n; ++i)
+    hrec[i] = make_double4(hx[i], dim > 1 ? hy[i] : 0.0, dim > 2 ? hz[i] : 0.0, hv[i]);
+  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_rec_orig, hrec, sizeof(double4) * (size_t)n, cudaMemcpyHostToDevice, st));
   GSK_CUDA_CHECK(ctx, cudaMemsetAsync(counts, 0, sizeof(int) * (size_t)ncells * 2, st));
 
   b.rec = ctx->d_rec_sorted;
   b.cell_start = ctx->d_cell_start;
   const int TB = 256;
   unsigned gn = (unsigned)((n + TB - 1) / TB);
-  pack_and_count_kernel<<<gn, TB, 0, st>>>(dx, dim > 1 ? dy : nullptr, dim > 2 ? dz : nullptr, dv, n, b,
-                                          ctx->d_rec_orig, cell_of, counts);
+  count_kernel<<<gn, TB, 0, st>>>(ctx->d_rec_orig, n, b, cell_of, counts);
   scan_kernel<<<1, 1024, 0, st>>>(counts, ncells, ctx->d_cell_start);
   scatter_kernel<<<gn, TB, 0, st>>>(ctx->d_rec_orig, cell_of, n, ctx->d_cell_start, cursor, ctx->d_rec_sorted);
   cell_sort_kernel<<<(unsigned)((ncells + TB - 1) / TB), TB, 0, st>>>(ctx->d_rec_sorted, ctx->d_cell_start, ncells);
   GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  // the pinned staging buffer is reused by the next plan: wait for the upload (kernels may still run)
   GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-  cudaFree(tmp);
-  cudaFree(cell_of);
-  cudaFree(counts);
   ctx->bins = b;
   return GSK_OK;
 }

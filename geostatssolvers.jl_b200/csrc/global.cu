@@ -515,9 +515,7 @@ struct GlobalPlan {
 void gsk_global_free(gsk_ctx *ctx) {
   GlobalPlan *g = ctx->gplan;
   if (!g) return;
-  cudaFree(g->A); cudaFree(g->X); cudaFree(g->Dinv); cudaFree(g->E); cudaFree(g->YE); cudaFree(g->GEE);
-  cudaFree(g->Bm); cudaFree(g->partial);
-  delete g;
+  delete g;  // the device buffers are cached in the context (gsk_buf)
   ctx->gplan = nullptr;
 }
 
@@ -542,16 +540,17 @@ int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const doub
       return GSK_ERR_INVALID;
     }
   }
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&ctx->d_rec_orig, sizeof(double4) * (size_t)n));
+  int rc;
+  if ((rc = gsk_buf(ctx, BUF_REC_ORIG, sizeof(double4) * (size_t)n, (void **)&ctx->d_rec_orig)) != GSK_OK) return rc;
   GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_rec_orig, rec.data(), sizeof(double4) * (size_t)n, cudaMemcpyHostToDevice, st));
   GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
 
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->A, sizeof(double) * (size_t)np * np));
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->X, sizeof(double) * (size_t)np * np));
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->Dinv, sizeof(double) * (size_t)nblk * NB * NB));
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->E, sizeof(double) * (size_t)np * g->ne));
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->YE, sizeof(double) * (size_t)np * g->ne));
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->GEE, sizeof(double) * (size_t)g->ne * g->ne));
+  if ((rc = gsk_buf(ctx, BUF_G_A, sizeof(double) * (size_t)np * np, (void **)&g->A)) != GSK_OK) return rc;
+  if ((rc = gsk_buf(ctx, BUF_G_X, sizeof(double) * (size_t)np * np, (void **)&g->X)) != GSK_OK) return rc;
+  if ((rc = gsk_buf(ctx, BUF_G_DINV, sizeof(double) * (size_t)nblk * NB * NB, (void **)&g->Dinv)) != GSK_OK) return rc;
+  if ((rc = gsk_buf(ctx, BUF_G_E, sizeof(double) * (size_t)np * g->ne, (void **)&g->E)) != GSK_OK) return rc;
+  if ((rc = gsk_buf(ctx, BUF_G_YE, sizeof(double) * (size_t)np * g->ne, (void **)&g->YE)) != GSK_OK) return rc;
+  if ((rc = gsk_buf(ctx, BUF_G_GEE, sizeof(double) * (size_t)g->ne * g->ne, (void **)&g->GEE)) != GSK_OK) return rc;
   GSK_CUDA_CHECK(ctx, cudaMemsetAsync(g->X, 0, sizeof(double) * (size_t)np * np, st));
 
   GArgs ga{ctx->d_rec_orig, n, np, ctx->vg, dim};
@@ -581,12 +580,10 @@ int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const doub
   gram_ee_kernel<<<1, 256, 0, st>>>(g->YE, np, g->ne, g->GEE);
   GSK_CUDA_CHECK(ctx, cudaGetLastError());
 
-  // batch of targets per GEMM: bound B to ~2 GB
+  // batch of targets per GEMM: bound B to ~2 GB (the buffers are sized in gsk_global_execute)
   long long batch = (long long)((2.0e9 / 8.0) / (double)np);
   batch = std::max<long long>(GT, std::min<long long>(batch, 32768) / GT * GT);
   g->batch = batch;
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->Bm, sizeof(double) * (size_t)np * batch));
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&g->partial, sizeof(double) * (size_t)(np / GT) * (1 + g->ne) * batch));
   GSK_CUDA_CHECK(ctx, cudaFuncSetAttribute(ygemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)YGEMM_SMEM));
   GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
   return GSK_OK;
@@ -600,6 +597,12 @@ int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, double *d
   const long long np = g->np;
   const int nblk = (int)(np / NB);
   GArgs ga{ctx->d_rec_orig, g->n, np, ctx->vg, ctx->prob.dim};
+  {
+    const long long bmax = std::min<long long>(g->batch, (count + GT - 1) / GT * GT);
+    int rc;
+    if ((rc = gsk_buf(ctx, BUF_G_BM, sizeof(double) * (size_t)np * bmax, (void **)&g->Bm)) != GSK_OK) return rc;
+    if ((rc = gsk_buf(ctx, BUF_G_PARTIAL, sizeof(double) * (size_t)(np / GT) * (1 + g->ne) * g->batch, (void **)&g->partial)) != GSK_OK) return rc;
+  }
   for (long long off = 0; off < count; off += g->batch) {
     const int nb = (int)std::min<long long>(g->batch, count - off);
     const int nbp = (nb + GT - 1) / GT * GT;

@@ -92,6 +92,13 @@ struct GskSearchArgs {
 // ---------------------------------------------------------------------------------------
 struct GlobalPlan;  // global.cu
 
+// cached device buffers: grown on demand, never shrunk, released in gsk_destroy — so that repeated
+// gsk_plan / gsk_krige calls do not pay cudaMalloc/cudaFree (which synchronise the device)
+enum GskBufId {
+  BUF_REC_ORIG, BUF_REC_SORTED, BUF_CELL_START, BUF_SUP, BUF_PTS0, BUF_PTS1, BUF_PTS2, BUF_CELL_OF, BUF_COUNTS,
+  BUF_G_A, BUF_G_X, BUF_G_DINV, BUF_G_E, BUF_G_YE, BUF_G_GEE, BUF_G_BM, BUF_G_PARTIAL, BUF_PEAK, BUF_COUNT
+};
+
 struct gsk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -126,12 +133,20 @@ struct gsk_ctx {
 
   GlobalPlan *gplan = nullptr;
 
+  void *bufp[BUF_COUNT] = {};
+  size_t bufcap[BUF_COUNT] = {};
+  void *h_stage = nullptr;  // pinned host staging buffer
+  size_t h_stage_cap = 0;
+
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   gsk_timing timing{};
   bool timing_pending = false;
   bool phase_timing = false;
 };
 
+// api.cu
+int gsk_buf(gsk_ctx *ctx, GskBufId id, size_t bytes, void **out);
+int gsk_host_stage(gsk_ctx *ctx, size_t bytes, void **out);
 // bins.cu
 int gsk_build_bins(gsk_ctx *ctx, const double *hx, const double *hy, const double *hz, const double *hv, long long n,
                    int dim, int k);
@@ -182,9 +197,9 @@ __device__ __forceinline__ double gsk_cov_rt(const GskVario &v, double d2) {
   }
 }
 
+// x^e for the drift monomials, e in {0, 1, 2} (Universal Kriging up to degree 2): branch-free
 __device__ __forceinline__ double gsk_ipow(double x, int e) {
-  double r = 1.0;
-  for (int i = 0; i < e; ++i) r *= x;
-  return r;
+  const double x1 = (e >= 1) ? x : 1.0;
+  return (e >= 2) ? x1 * x : x1;
 }
 #endif

@@ -444,26 +444,28 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
           f0[t2] = m;
         }
 #define GFF(i, j) GM[(2 + (i)) * EPr + 2 + (j)]
+        // Cholesky with reciprocal pivots (no FP64 divisions / sqrt sequences on the serial lane)
+        double dinv[GSK_MAX_DRIFT_TERMS];
         for (int j = 0; j < c; ++j) {
           double d = GFF(j, j);
-          for (int p = 0; p < j; ++p) d -= GFF(j, p) * GFF(j, p);
-          d = sqrt(d);
-          GFF(j, j) = d;
+          for (int p = 0; p < j; ++p) d = fma(-GFF(j, p), GFF(j, p), d);
+          const double ri = gsk_rsqrt(d);
+          dinv[j] = ri;
           for (int i = j + 1; i < c; ++i) {
             double s = GFF(i, j);
-            for (int p = 0; p < j; ++p) s -= GFF(i, p) * GFF(j, p);
-            GFF(i, j) = s / d;
+            for (int p = 0; p < j; ++p) s = fma(-GFF(i, p), GFF(j, p), s);
+            GFF(i, j) = s * ri;
           }
         }
         for (int j = 0; j < c; ++j) {
           double s = GM[(2 + j) * EPr + 0] - f0[j];
-          for (int p = 0; p < j; ++p) s -= GFF(j, p) * nu[p];
-          nu[j] = s / GFF(j, j);
+          for (int p = 0; p < j; ++p) s = fma(-GFF(j, p), nu[p], s);
+          nu[j] = s * dinv[j];
         }
         for (int j = c - 1; j >= 0; --j) {
           double s = nu[j];
-          for (int p = j + 1; p < c; ++p) s -= GFF(p, j) * nu[p];
-          nu[j] = s / GFF(j, j);
+          for (int p = j + 1; p < c; ++p) s = fma(-GFF(p, j), nu[p], s);
+          nu[j] = s * dinv[j];
         }
 #undef GFF
         double mz = 0.0, mb = 0.0, mf = 0.0;

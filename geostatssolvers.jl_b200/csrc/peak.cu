@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(256) dmma_kernel(double *out, int iters, doubl
 int gsk_peak_measure(gsk_ctx *ctx, double *dfma, double *dmma) {
   double *d_out = nullptr;
   const int blocks = ctx->sm_count * 8, threads = 256;
-  GSK_CUDA_CHECK(ctx, cudaMalloc(&d_out, sizeof(double) * blocks * threads));
+  int rc = gsk_buf(ctx, BUF_PEAK, sizeof(double) * blocks * threads, (void **)&d_out);
+  if (rc != GSK_OK) return rc;
   cudaEvent_t e0 = ctx->ev[3], e1 = ctx->ev[4];
   auto time_best = [&](auto launch) -> double {
     float best = 1e30f;
@@ -80,6 +81,5 @@ int gsk_peak_measure(gsk_ctx *ctx, double *dfma, double *dmma) {
   // per warp and mma: 16·8·16 FMAs
   *dmma = (double)blocks * (threads / 32) * (double)it2 * 4.0 * (16.0 * 8.0 * 16.0 * 2.0) / (ms2 * 1e-3) / 1e12;
   GSK_CUDA_CHECK(ctx, cudaGetLastError());
-  cudaFree(d_out);
   return GSK_OK;
 }
