@@ -268,7 +268,7 @@ def main():
     if rank == 0:
         flops_t = gskrige.synth.algorithmic_flops_per_target(spec)
         solve_ms = statistics.median(pv) if k else statistics.median(pv) or ms_per_step
-        nlaunch_solve = max(1, -(-count // (1 << 20))) if k else 1
+        nlaunch_solve = max(1, int(launches_per_step) // 2) if k else 1   # one search + one solve launch per chunk
         extra = {}
         if k:
             achieved = flops_t * count / (solve_ms * 1e-3) / 1e12          # all solve launches of a step together

@@ -116,6 +116,12 @@ extern "C" GSK_API int gsk_create(gsk_ctx **out, int device_id) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   ctx->own_stream = true;
   for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&ctx->ev_search[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_solve[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     std::string m = cudaGetErrorString(e);
     delete ctx;
@@ -182,6 +188,12 @@ extern "C" GSK_API void gsk_destroy(gsk_ctx *ctx) {
   for (int i = 0; i < 6; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_search[i]) cudaEventDestroy(ctx->ev_search[i]);
+    if (ctx->ev_solve[i]) cudaEventDestroy(ctx->ev_solve[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   delete ctx;
 }
 
@@ -357,10 +369,9 @@ static int ensure(gsk_ctx *ctx, void **buf, size_t *cap, size_t bytes) {
 
 static long long local_chunk_targets() {
   static long long v = 0;
-  if (!v) {
+  if (v == 0) {
     const char *s = getenv("GSK_CHUNK_TARGETS");
-    v = s ? atoll(s) : (1ll << 20);
-    if (v < 1024) v = 1024;
+    v = s ? std::max<long long>(1024, atoll(s)) : -1;  // -1: automatic
   }
   return v;
 }
@@ -382,33 +393,67 @@ extern "C" GSK_API int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count, d
     if (rc != GSK_OK) return rc;
   } else {
     const int k = ctx->prob.max_neighbors;
-    const long long chunk = std::min<long long>(local_chunk_targets(), std::max<long long>(count, 1));
+    // chunks of ~1M targets bound the neighbour-list scratch (4k+4 B per target); chunk edges are aligned
+    // to whole tile layers of the grid where that is cheap. GSK_OVERLAP=1 runs the search of chunk c+1 on
+    // a side stream while chunk c is solved (measured on B200: no gain — both kernels already fill the
+    // SMs and small chunks add tail effects — so it is off by default).
+    static const bool want_overlap = getenv("GSK_OVERLAP") != nullptr;
+    long long chunk = local_chunk_targets();
+    if (chunk <= 0) {
+      chunk = 1ll << 20;
+      if (ctx->tg.is_grid) {
+        const int dim = ctx->tg.dim;
+        long long unit = (dim == 3) ? ctx->tg.gdim[0] * ctx->tg.gdim[1] * 4 : (dim == 2 ? ctx->tg.gdim[0] * 8 : 128);
+        if (unit <= (1ll << 21)) chunk = (chunk + unit - 1) / unit * unit;
+      }
+    }
+    chunk = std::min<long long>(chunk, std::max<long long>(count, 1));
+    const bool overlap = want_overlap && !phase_timing && count > chunk;
+    const int nbuf = overlap ? 2 : 1;
     if (!d_nneigh) {
-      rc = ensure(ctx, (void **)&ctx->d_nn, &ctx->cap_nn, sizeof(int) * (size_t)chunk);
+      rc = ensure(ctx, (void **)&ctx->d_nn, &ctx->cap_nn, sizeof(int) * (size_t)chunk * nbuf);
       if (rc != GSK_OK) return rc;
     }
     if (!d_neigh_idx) {
-      rc = ensure(ctx, (void **)&ctx->d_nbr, &ctx->cap_nbr, sizeof(int) * (size_t)chunk * k);
+      rc = ensure(ctx, (void **)&ctx->d_nbr, &ctx->cap_nbr, sizeof(int) * (size_t)chunk * k * nbuf);
       if (rc != GSK_OK) return rc;
     }
-    for (long long off = 0; off < count; off += chunk) {
+    if (overlap) {
+      GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+      GSK_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    }
+    long long c = 0;
+    for (long long off = 0; off < count; off += chunk, ++c) {
       const long long cnt = std::min<long long>(chunk, count - off);
-      int *nn = d_nneigh ? d_nneigh + off : ctx->d_nn;
-      int *nbr = d_neigh_idx ? d_neigh_idx + off * k : ctx->d_nbr;
+      const int b = (int)(c % nbuf);
+      int *nn = d_nneigh ? d_nneigh + off : ctx->d_nn + (size_t)b * chunk;
+      int *nbr = d_neigh_idx ? d_neigh_idx + off * k : ctx->d_nbr + (size_t)b * chunk * k;
+      if (overlap) {
+        // the scratch of parity b is free once the solve of chunk c-2 has read it
+        if (c >= 2) GSK_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_solve[b], 0));
+        rc = gsk_launch_search(ctx, ctx->stream2, first + off, cnt, nn, nbr, &launches);
+        if (rc != GSK_OK) return rc;
+        GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_search[b], ctx->stream2));
+        GSK_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_search[b], 0));
+        rc = gsk_launch_local_solve(ctx, ctx->stream, first + off, cnt, nn, nbr, d_mean + off, d_var + off, &launches);
+        if (rc != GSK_OK) return rc;
+        GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_solve[b], ctx->stream));
+        continue;
+      }
       if (phase_timing) cudaEventRecord(ctx->ev[3], ctx->stream);
-      rc = gsk_launch_search(ctx, first + off, cnt, nn, nbr, &launches);
+      rc = gsk_launch_search(ctx, ctx->stream, first + off, cnt, nn, nbr, &launches);
       if (rc != GSK_OK) return rc;
       if (phase_timing) cudaEventRecord(ctx->ev[4], ctx->stream);
-      rc = gsk_launch_local_solve(ctx, first + off, cnt, nn, nbr, d_mean + off, d_var + off, &launches);
+      rc = gsk_launch_local_solve(ctx, ctx->stream, first + off, cnt, nn, nbr, d_mean + off, d_var + off, &launches);
       if (rc != GSK_OK) return rc;
       if (phase_timing) {
         cudaEventRecord(ctx->ev[5], ctx->stream);
         cudaEventSynchronize(ctx->ev[5]);
-        float a = 0.f, b = 0.f;
+        float a = 0.f, b2 = 0.f;
         cudaEventElapsedTime(&a, ctx->ev[3], ctx->ev[4]);
-        cudaEventElapsedTime(&b, ctx->ev[4], ctx->ev[5]);
+        cudaEventElapsedTime(&b2, ctx->ev[4], ctx->ev[5]);
         ms_search += a;
-        ms_solve += b;
+        ms_solve += b2;
       }
     }
   }

@@ -101,8 +101,10 @@ enum GskBufId {
 
 struct gsk_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // main stream: solve kernels, copies (may be the caller's)
   bool own_stream = false;
+  cudaStream_t stream2 = nullptr;  // side stream: the search of chunk c+1 overlaps the solve of chunk c
+  cudaEvent_t ev_search[2] = {nullptr, nullptr}, ev_solve[2] = {nullptr, nullptr}, ev_fork = nullptr;
   std::string err;
   int sm_count = 148;
 
@@ -151,10 +153,11 @@ int gsk_host_stage(gsk_ctx *ctx, size_t bytes, void **out);
 int gsk_build_bins(gsk_ctx *ctx, const double *hx, const double *hy, const double *hz, const double *hv, long long n,
                    int dim, int k);
 // search.cu
-int gsk_launch_search(gsk_ctx *ctx, long long first, long long count, int *d_nn, int *d_nbr, int *launches);
+int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long count, int *d_nn, int *d_nbr,
+                      int *launches);
 // local_solve*.cu
-int gsk_launch_local_solve(gsk_ctx *ctx, long long first, long long count, const int *d_nn, const int *d_nbr,
-                           double *d_mean, double *d_var, int *launches);
+int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long long count, const int *d_nn,
+                           const int *d_nbr, double *d_mean, double *d_var, int *launches);
 // global.cu
 int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const double *hz, const double *hv);
 int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, double *d_mean, double *d_var, int *d_nn,

@@ -3,8 +3,8 @@
 
 #include "local_solve_small.cuh"
 
-int gsk_launch_local_solve(gsk_ctx *ctx, long long first, long long count, const int *d_nn, const int *d_nbr,
-                           double *d_mean, double *d_var, int *launches) {
+int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long long count, const int *d_nn,
+                           const int *d_nbr, double *d_mean, double *d_var, int *launches) {
   GskLocalArgs a{};
   a.tg = ctx->tg;
   a.vg = ctx->vg;
@@ -29,12 +29,12 @@ int gsk_launch_local_solve(gsk_ctx *ctx, long long first, long long count, const
   cudaError_t err;
   static const bool no_small = getenv("GSK_NO_SMALL_KERNEL") != nullptr;  // development switch
   if (!no_small && a.k <= gsk_local::SK_KMAX && (ctx->es.kind == GSK_EST_SIMPLE || ctx->es.nterms == 1))
-    err = gsk_local_launch_small(a, ctx->stream);
-  else if (rows(4) <= 12) err = gsk_local_launch_A(a, e, ctx->stream);
-  else if (rows(4) <= 24) err = gsk_local_launch_B(a, e, ctx->stream);
-  else if (rows(8) <= 40) err = gsk_local_launch_C(a, e, ctx->stream);
-  else if (rows(8) <= 72) err = gsk_local_launch_D(a, e, ctx->stream);
-  else if (rows(8) <= 112) err = gsk_local_launch_E(a, e, ctx->stream);
+    err = gsk_local_launch_small(a, st);
+  else if (rows(4) <= 12) err = gsk_local_launch_A(a, e, st);
+  else if (rows(4) <= 24) err = gsk_local_launch_B(a, e, st);
+  else if (rows(8) <= 40) err = gsk_local_launch_C(a, e, st);
+  else if (rows(8) <= 72) err = gsk_local_launch_D(a, e, st);
+  else if (rows(8) <= 112) err = gsk_local_launch_E(a, e, st);
   else {
     ctx->err = "max_neighbors too large for the local kernels";
     return GSK_ERR_UNSUPPORTED;

@@ -321,7 +321,8 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
 
 }  // namespace
 
-int gsk_launch_search(gsk_ctx *ctx, long long first, long long count, int *d_nn, int *d_nbr, int *launches) {
+int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long count, int *d_nn, int *d_nbr,
+                      int *launches) {
   GskSearchArgs a{};
   a.tg = ctx->tg;
   a.bins = ctx->bins;
@@ -367,13 +368,13 @@ int gsk_launch_search(gsk_ctx *ctx, long long first, long long count, int *d_nn,
   cudaError_t e;
   if (dim == 1) {
     e = cudaFuncSetAttribute(search_kernel<NT, 1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) search_kernel<NT, 1, 1, 1><<<nblocks, NT, smem, ctx->stream>>>(a);
+    if (e == cudaSuccess) search_kernel<NT, 1, 1, 1><<<nblocks, NT, smem, st>>>(a);
   } else if (dim == 2) {
     e = cudaFuncSetAttribute(search_kernel<16, 8, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) search_kernel<16, 8, 1, 2><<<nblocks, NT, smem, ctx->stream>>>(a);
+    if (e == cudaSuccess) search_kernel<16, 8, 1, 2><<<nblocks, NT, smem, st>>>(a);
   } else {
     e = cudaFuncSetAttribute(search_kernel<8, 4, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) search_kernel<8, 4, 4, 3><<<nblocks, NT, smem, ctx->stream>>>(a);
+    if (e == cudaSuccess) search_kernel<8, 4, 4, 3><<<nblocks, NT, smem, st>>>(a);
   }
   GSK_CUDA_CHECK(ctx, e);
   GSK_CUDA_CHECK(ctx, cudaGetLastError());
