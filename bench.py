@@ -154,6 +154,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="targets per step of the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--targets", type=int, default=0, help="limit the per-rank slab (debug)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "multicast", "nccl"],
+                    help="N>1 result gather: stores into every rank's symmetric-memory buffer fused in the solve kernel "
+                         "(peer), the same through one NVLS multicast store (multicast), or an NCCL all-gather (nccl)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -189,12 +192,40 @@ def main():
     plan_ms = ctx.timing()["ms_plan"]
     d_mean = torch.empty(count, dtype=torch.float64, device=dev)
     d_var = torch.empty(count, dtype=torch.float64, device=dev)
+    gather_mode = "single GPU"
+    hdl = None
     if world > 1:
-        g_mean = torch.empty(count * world, dtype=torch.float64, device=dev)
-        g_var = torch.empty(count * world, dtype=torch.float64, device=dev)
+        Tall = count * world
+        if args.gather != "nccl":
+            # fused gather: the solve kernel stores every result into all ranks' buffers over NVLink
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                sbuf = symm_mem.empty(2 * Tall, dtype=torch.float64, device=dev)
+                hdl = symm_mem.rendezvous(sbuf, dist.group.WORLD)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                mean_ptrs, var_ptrs, use_mc = ptrs, [p + 8 * Tall for p in ptrs], False
+                if args.gather == "multicast":
+                    mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+                    if mc:
+                        mean_ptrs, var_ptrs, use_mc = [mc], [mc + 8 * Tall], True
+                gather_mode = ("results stored by the compute kernels into every rank's symmetric-memory buffer over NVLink "
+                               + ("(one NVLS multicast store per value)" if use_mc else "(P2P stores to each peer)")
+                               + ", device-side barrier per step")
+            except Exception as exc:  # noqa: BLE001 - fall back to NCCL, say so in the JSON line
+                hdl = None
+                gather_mode = f"NCCL all-gather (symmetric memory unavailable: {type(exc).__name__})"
+        if hdl is None:
+            g_mean = torch.empty(Tall, dtype=torch.float64, device=dev)
+            g_var = torch.empty(Tall, dtype=torch.float64, device=dev)
+            if args.gather == "nccl":
+                gather_mode = "NCCL all-gather of mean and variance inside the timed step"
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
 
     def step():
+        if hdl is not None:
+            ctx.execute_peers(first, count, mean_ptrs, var_ptrs, out_offset=rank * count, multicast=use_mc)
+            hdl.barrier(channel=0)                   # every rank's stores have landed everywhere
+            return
         ctx.execute(first, count, d_mean.data_ptr(), d_var.data_ptr())
         if world > 1:                                # result gather: NCCL all-gather over NVLink
             dist.all_gather_into_tensor(g_mean, d_mean)
@@ -231,6 +262,17 @@ def main():
     ms_per_step = dev_ms / args.steps
     value = count * world / (ms_per_step * 1e-3)
 
+    if hdl is not None:
+        # the gathered field must be identical on every rank and hold this rank's slab at its place
+        ctx.execute(first, count, d_mean.data_ptr(), d_var.data_ptr())
+        torch.cuda.synchronize()
+        full_mean = sbuf[:count * world]
+        assert torch.equal(full_mean[rank * count:(rank + 1) * count], d_mean), "fused gather: own slab differs"
+        chk = torch.stack([full_mean.sum(), sbuf[count * world:].sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo, hi), "fused gather: ranks hold different gathered fields"
+
     # ---- dominant kernel, timed live with events around each launch (extra steps, not part of `value`) ----
     ctx.set_phase_timing(True)
     ps, pv = [], []
@@ -263,6 +305,9 @@ def main():
     e2e_s = float(te.item())
     h2d = spec.n_samples * (spec.dim + 1) * 8 + 3 * spec.support[0].shape[0] * 8
     d2h = 16 * count
+    if hdl is None:
+        ctx.execute(first, count, d_mean.data_ptr(), d_var.data_ptr())
+        torch.cuda.synchronize()
     assert np.array_equal(h_mean, d_mean.cpu().numpy()), "e2e and resident paths disagree"
 
     if rank == 0:
@@ -293,7 +338,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.config, spec), "targets_per_gpu": count, "l2": "flushed between timed steps (256 MB write)",
-                       "multi_gpu": "slabs of the slowest axis, samples replicated, NCCL all-gather of mean+variance in the timed step" if world > 1 else "single GPU"},
+                       "multi_gpu": ("slabs of the slowest axis, samples replicated; " + gather_mode) if world > 1 else "single GPU"},
             "clocks": clocks,
             "e2e": {"value": count * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3, "api": "gsk_krige (C ABI, pinned host buffers; includes sample upload + bin build)"},

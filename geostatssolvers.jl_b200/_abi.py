@@ -236,6 +236,9 @@ def load_library(path: os.PathLike | None = None):
     lib.gsk_plan.restype = C.c_int
     lib.gsk_execute.argtypes = [ctx, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gsk_execute.restype = C.c_int
+    lib.gsk_execute_peers.argtypes = [ctx, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                      C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
+    lib.gsk_execute_peers.restype = C.c_int
     lib.gsk_get_timing.argtypes = [ctx, C.POINTER(GskTiming)]
     lib.gsk_get_timing.restype = C.c_int
     lib.gsk_set_phase_timing.argtypes = [ctx, C.c_int]
@@ -257,7 +260,7 @@ def load_library(path: os.PathLike | None = None):
 
 EXPORTED_SYMBOLS = [
     "gsk_create", "gsk_destroy", "gsk_last_error", "gsk_set_stream", "gsk_synchronize", "gsk_krige", "gsk_plan",
-    "gsk_execute", "gsk_get_timing", "gsk_set_phase_timing", "gsk_num_targets", "gsk_uk_exponents", "gsk_default_support",
+    "gsk_execute", "gsk_execute_peers", "gsk_get_timing", "gsk_set_phase_timing", "gsk_num_targets", "gsk_uk_exponents", "gsk_default_support",
     "gsk_measure_fp64_peak", "gsk_abi_version",
 ]
 
@@ -324,6 +327,14 @@ class Context:
         self._check(self.lib.gsk_execute(self._h, int(first), int(count), C.c_void_p(d_mean), C.c_void_p(d_var),
                                          C.c_void_p(d_nneigh) if d_nneigh else None,
                                          C.c_void_p(d_idx) if d_idx else None))
+
+    def execute_peers(self, first, count, mean_ptrs, var_ptrs, out_offset=0, multicast=False):
+        """Like :meth:`execute`, but every result is stored into all peer-mapped buffers (fused gather)."""
+        n = len(mean_ptrs)
+        mp = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in mean_ptrs])
+        vp = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in var_ptrs])
+        self._check(self.lib.gsk_execute_peers(self._h, int(first), int(count), n, mp, vp, int(out_offset),
+                                               int(bool(multicast)), None, None))
 
     def set_stream(self, cuda_stream: int):
         self._check(self.lib.gsk_set_stream(self._h, C.c_void_p(cuda_stream)))

@@ -376,12 +376,40 @@ static long long local_chunk_targets() {
   return v;
 }
 
+static int execute_impl(gsk_ctx *ctx, int64_t first, int64_t count, int32_t *d_nneigh, int32_t *d_neigh_idx);
+
 extern "C" GSK_API int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count, double *d_mean, double *d_var,
                            int32_t *d_nneigh, int32_t *d_neigh_idx) {
   if (!ctx) return GSK_ERR_INVALID;
+  if (!d_mean || !d_var) return fail(ctx, GSK_ERR_INVALID, "output buffers are NULL");
+  ctx->out = GskOut{};
+  ctx->out.n = 1;
+  ctx->out.mean[0] = d_mean;
+  ctx->out.var[0] = d_var;
+  return execute_impl(ctx, first, count, d_nneigh, d_neigh_idx);
+}
+
+extern "C" GSK_API int gsk_execute_peers(gsk_ctx *ctx, int64_t first, int64_t count, int n_peers,
+                                 double *const *d_mean_peers, double *const *d_var_peers, int64_t out_offset,
+                                 int multicast, int32_t *d_nneigh, int32_t *d_neigh_idx) {
+  if (!ctx) return GSK_ERR_INVALID;
+  if (n_peers < 1 || n_peers > GSK_MAX_PEERS || !d_mean_peers || !d_var_peers)
+    return fail(ctx, GSK_ERR_INVALID, "n_peers must be in [1, 8] with non-NULL pointer lists");
+  if (multicast && n_peers != 1) return fail(ctx, GSK_ERR_INVALID, "multicast takes exactly one (multicast) address per field");
+  ctx->out = GskOut{};
+  ctx->out.n = n_peers;
+  ctx->out.multicast = multicast ? 1 : 0;
+  for (int p = 0; p < n_peers; ++p) {
+    if (!d_mean_peers[p] || !d_var_peers[p]) return fail(ctx, GSK_ERR_INVALID, "peer output buffer is NULL");
+    ctx->out.mean[p] = d_mean_peers[p] + out_offset;
+    ctx->out.var[p] = d_var_peers[p] + out_offset;
+  }
+  return execute_impl(ctx, first, count, d_nneigh, d_neigh_idx);
+}
+
+static int execute_impl(gsk_ctx *ctx, int64_t first, int64_t count, int32_t *d_nneigh, int32_t *d_neigh_idx) {
   if (!ctx->planned) return fail(ctx, GSK_ERR_STATE, "gsk_execute called before gsk_plan");
   if (first < 0 || count < 0 || first + count > ctx->n_targets) return fail(ctx, GSK_ERR_INVALID, "target range out of bounds");
-  if (!d_mean || !d_var) return fail(ctx, GSK_ERR_INVALID, "output buffers are NULL");
   GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   const bool phase_timing = ctx->phase_timing;
   int launches = 0;
@@ -389,7 +417,7 @@ extern "C" GSK_API int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count, d
   GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
   int rc = GSK_OK;
   if (ctx->prob.max_neighbors == 0) {
-    rc = gsk_global_execute(ctx, first, count, d_mean, d_var, d_nneigh, &launches);
+    rc = gsk_global_execute(ctx, first, count, d_nneigh, &launches);
     if (rc != GSK_OK) return rc;
   } else {
     const int k = ctx->prob.max_neighbors;
@@ -435,7 +463,7 @@ extern "C" GSK_API int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count, d
         if (rc != GSK_OK) return rc;
         GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_search[b], ctx->stream2));
         GSK_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_search[b], 0));
-        rc = gsk_launch_local_solve(ctx, ctx->stream, first + off, cnt, nn, nbr, d_mean + off, d_var + off, &launches);
+        rc = gsk_launch_local_solve(ctx, ctx->stream, first + off, cnt, nn, nbr, off, &launches);
         if (rc != GSK_OK) return rc;
         GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_solve[b], ctx->stream));
         continue;
@@ -444,7 +472,7 @@ extern "C" GSK_API int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count, d
       rc = gsk_launch_search(ctx, ctx->stream, first + off, cnt, nn, nbr, &launches);
       if (rc != GSK_OK) return rc;
       if (phase_timing) cudaEventRecord(ctx->ev[4], ctx->stream);
-      rc = gsk_launch_local_solve(ctx, ctx->stream, first + off, cnt, nn, nbr, d_mean + off, d_var + off, &launches);
+      rc = gsk_launch_local_solve(ctx, ctx->stream, first + off, cnt, nn, nbr, off, &launches);
       if (rc != GSK_OK) return rc;
       if (phase_timing) {
         cudaEventRecord(ctx->ev[5], ctx->stream);

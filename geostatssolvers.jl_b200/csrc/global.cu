@@ -423,8 +423,7 @@ __global__ void __launch_bounds__(256, 1) ygemm_dmma_kernel(const double *__rest
 // ---- per-target epilogue: reduce the partials over the row tiles, then the e×e algebra ----
 __global__ void global_epilogue_kernel(const double *__restrict__ partial, int nmt, int ne, long long nbpad,
                                        int nbatch, const double *__restrict__ GEE, GskEstimator es, GskTargets tg,
-                                       double sill, unsigned flags, long long first, double *__restrict__ mean,
-                                       double *__restrict__ var) {
+                                       double sill, unsigned flags, long long first, GskOut out) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nbatch) return;
   double g[2 + GSK_MAX_DRIFT_TERMS];
@@ -490,8 +489,7 @@ __global__ void global_epilogue_kernel(const double *__restrict__ partial, int n
   }
   if (flags & GSK_FLAG_CLAMP_VARIANCE) s2 = (s2 > 0.0 || s2 != s2) ? s2 : 0.0;
   if (flags & GSK_FLAG_SQRT_ROUNDTRIP) { double sd = sqrt(s2); s2 = sd * sd; }
-  mean[t] = mu;
-  var[t] = s2;
+  gsk_store_result(out, t, mu, s2);
 }
 
 __global__ void fill_int_kernel(int *p, long long n, int v) {
@@ -589,8 +587,7 @@ int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const doub
   return GSK_OK;
 }
 
-int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, double *d_mean, double *d_var, int *d_nn,
-                       int *launches) {
+int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, int *d_nn, int *launches) {
   GlobalPlan *g = ctx->gplan;
   if (!g) { ctx->err = "global plan missing"; return GSK_ERR_STATE; }
   cudaStream_t st = ctx->stream;
@@ -620,11 +617,16 @@ int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, double *d
         rhs_kernel<GSK_VARIO_EXPONENTIAL><<<grid, 256, 0, st>>>(ga, ctx->tg, ctx->d_sup, ctx->prob.n_support, first + off, nb, g->Bm);
         break;
     }
+    GskOut out_b = ctx->out;
+    for (int p = 0; p < out_b.n; ++p) {
+      out_b.mean[p] += off;
+      out_b.var[p] += off;
+    }
     ygemm_dmma_kernel<<<dim3((unsigned)(nbp / GT), (unsigned)(np / GT)), 256, YGEMM_SMEM, st>>>(
         g->X, np, g->Bm, g->YE, g->ne, g->batch, g->partial);
     global_epilogue_kernel<<<(nb + 127) / 128, 128, 0, st>>>(g->partial, (int)(np / GT), g->ne, g->batch, nb, g->GEE, ctx->es,
                                                              ctx->tg, ctx->vg.sill, ctx->prob.flags, first + off,
-                                                             d_mean + off, d_var + off);
+                                                             out_b);
     if (launches) *launches += 3;
   }
   if (d_nn) {

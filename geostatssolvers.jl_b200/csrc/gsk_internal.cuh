@@ -54,6 +54,18 @@ struct GskEstimator {
   int exps[GSK_MAX_DRIFT_TERMS][3];
 };
 
+// Where results go. n == 1: one buffer (the caller's). n > 1: the same value is stored into every peer's
+// buffer over NVLink (peer-mapped pointers, e.g. torch symmetric memory) — the result "gather" is fused
+// into the epilogue of the compute kernel. multicast: out[0] is an NVLS multicast address and one
+// multimem.st reaches all peers through the switch.
+#define GSK_MAX_PEERS 8
+struct GskOut {
+  int n;
+  int multicast;
+  double *mean[GSK_MAX_PEERS];
+  double *var[GSK_MAX_PEERS];
+};
+
 struct GskLocalArgs {
   GskTargets tg;
   GskVario vg;
@@ -69,7 +81,7 @@ struct GskLocalArgs {
   long long first, count;   // slab
   const int *nn;            // neighbours per target (slab-local)
   const int *nbr;           // count × k original indices, −1 padded
-  double *mean, *var;       // slab-local outputs
+  GskOut out;               // outputs, indexed by slab-local target (pointers already offset)
 };
 
 struct GskSearchArgs {
@@ -144,6 +156,7 @@ struct gsk_ctx {
   gsk_timing timing{};
   bool timing_pending = false;
   bool phase_timing = false;
+  GskOut out{};  // destination of the running gsk_execute / gsk_execute_peers
 };
 
 // api.cu
@@ -157,11 +170,10 @@ int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long 
                       int *launches);
 // local_solve*.cu
 int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long long count, const int *d_nn,
-                           const int *d_nbr, double *d_mean, double *d_var, int *launches);
+                           const int *d_nbr, long long out_off, int *launches);
 // global.cu
 int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const double *hz, const double *hv);
-int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, double *d_mean, double *d_var, int *d_nn,
-                       int *launches);
+int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, int *d_nn, int *launches);
 void gsk_global_free(gsk_ctx *ctx);
 // peak.cu
 int gsk_peak_measure(gsk_ctx *ctx, double *dfma, double *dmma);
@@ -201,6 +213,22 @@ __device__ __forceinline__ double gsk_cov_rt(const GskVario &v, double d2) {
 }
 
 // x^e for the drift monomials, e in {0, 1, 2} (Universal Kriging up to degree 2): branch-free
+// store one target's result into every destination (see GskOut)
+__device__ __forceinline__ void gsk_store_result(const GskOut &o, long long t, double m, double v) {
+  if (o.multicast) {
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(o.mean[0] + t), "d"(m) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(o.var[0] + t), "d"(v) : "memory");
+    return;
+  }
+#pragma unroll
+  for (int p = 0; p < GSK_MAX_PEERS; ++p) {
+    if (p < o.n) {
+      o.mean[p][t] = m;
+      o.var[p][t] = v;
+    }
+  }
+}
+
 __device__ __forceinline__ double gsk_ipow(double x, int e) {
   const double x1 = (e >= 1) ? x : 1.0;
   return (e >= 2) ? x1 * x : x1;

@@ -4,7 +4,7 @@
 #include "local_solve_small.cuh"
 
 int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long long count, const int *d_nn,
-                           const int *d_nbr, double *d_mean, double *d_var, int *launches) {
+                           const int *d_nbr, long long out_off, int *launches) {
   GskLocalArgs a{};
   a.tg = ctx->tg;
   a.vg = ctx->vg;
@@ -21,8 +21,11 @@ int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long 
   a.count = count;
   a.nn = d_nn;
   a.nbr = d_nbr;
-  a.mean = d_mean;
-  a.var = d_var;
+  a.out = ctx->out;
+  for (int p = 0; p < a.out.n; ++p) {
+    a.out.mean[p] += out_off;
+    a.out.var[p] += out_off;
+  }
   // extra rows: b, z, then the c drift rows
   const int e = 2 + ctx->es.nterms;
   auto rows = [&](int W) { return (a.k + W - 1) / W * W + (e + W - 1) / W * W; };

@@ -233,8 +233,7 @@ __global__ void __launch_bounds__(128, 3) local_solve_small_kernel(const GskLoca
       if (a.flags & GSK_FLAG_CLAMP_VARIANCE) var = (var > 0.0 || var != var) ? var : 0.0;
       if (a.flags & GSK_FLAG_SQRT_ROUNDTRIP) { double sd = sqrt(var); var = sd * sd; }
     }
-    a.mean[t] = mean;
-    a.var[t] = var;
+    gsk_store_result(a.out, t, mean, var);
   }
 }
 

@@ -154,6 +154,13 @@ GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *prob);
  * asynchronous on the context stream */
 GSK_API int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count,
                 double *d_mean, double *d_var, int32_t *d_nneigh, int32_t *d_neigh_idx);
+/* same, with the result gather fused into the compute kernels: every target's mean/variance is stored
+ * into n_peers peer-mapped buffers (NVLink P2P pointers valid in this process, e.g. from CUDA IPC / torch
+ * symmetric memory) at index out_offset + (target - first). multicast != 0: n_peers must be 1 and the
+ * pointers are NVLS multicast addresses (one multimem.st per value reaches every peer through NVSwitch). */
+GSK_API int gsk_execute_peers(gsk_ctx *ctx, int64_t first, int64_t count, int n_peers,
+                              double *const *d_mean_peers, double *const *d_var_peers, int64_t out_offset,
+                              int multicast, int32_t *d_nneigh, int32_t *d_neigh_idx);
 GSK_API int gsk_get_timing(const gsk_ctx *ctx, gsk_timing *out);
 /* when on, gsk_execute brackets every search / solve launch with CUDA events (and synchronises on them)
  * so that gsk_timing.ms_search / ms_solve are filled; off by default (no synchronisation in gsk_execute) */
