@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="targets per step of the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--targets", type=int, default=0, help="limit the per-rank slab (debug)")
-    ap.add_argument("--gather", default="peer", choices=["peer", "multicast", "nccl"],
+    ap.add_argument("--gather", default="multicast", choices=["peer", "multicast", "nccl"],
                     help="N>1 result gather: stores into every rank's symmetric-memory buffer fused in the solve kernel "
                          "(peer), the same through one NVLS multicast store (multicast), or an NCCL all-gather (nccl)")
     args = ap.parse_args()
