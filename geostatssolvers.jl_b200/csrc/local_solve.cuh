@@ -31,7 +31,7 @@ namespace gsk_local {
 
 
 template <int W>
-__host__ __device__ constexpr int col_align() { return W == 8 ? 8 : 4; }
+__host__ __device__ constexpr int col_align() { return W >= 8 ? 8 : 4; }
 
 // doubles stored before column p: Σ_{j<p} (RT − (j & ~(A−1)))
 template <int RT, int A>
@@ -358,8 +358,27 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
 #pragma unroll
         for (int p = 0; p < c0; ++p) update(p);
       } else {
+        // runtime loop with an incrementally advanced column pointer: base(p+1) − base(p) = RT − s_{p+1}
+        const double *colp = S;
 #pragma unroll 2
-        for (int p = 0; p < c0; ++p) update(p);
+        for (int p = 0; p < c0; ++p) {
+          double piv[W];
+#pragma unroll
+          for (int jj = 0; jj < W; jj += 2) {
+            const double2 t2 = *reinterpret_cast<const double2 *>(colp + c0 + jj);
+            piv[jj] = t2.x;
+            piv[jj + 1] = t2.y;
+          }
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if (r >= rmin) {
+              const double own = GSK_ROW_OK(r) ? colp[r * G + l] : 0.0;
+#pragma unroll
+              for (int jj = 0; jj < W; ++jj) acc[r][jj] = fma(-own, piv[jj], acc[r][jj]);
+            }
+          }
+          colp += RT - ((p + 1) & ~(A - 1));
+        }
       }
       // the W×W panel: pivots and row entries are exchanged by shuffles inside the group
 #pragma unroll
@@ -399,9 +418,9 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
         for (int jj = 0; jj < W; ++jj) g[jj] = 0.0;
         const int i = r * G + l;
         const bool mine = i >= KC && i < KC + EPr;
+        const double *col = S;
 #pragma unroll 4
-        for (int p = 0; p < KC; ++p) {
-          const double *col = S + col_off<RT, A>(p) - (p & ~(A - 1));
+        for (int p = 0; p < KC; ++p, col += RT - (p & ~(A - 1))) {
           const double own = mine ? col[i] : 0.0;
 #pragma unroll
           for (int jj = 0; jj < W; jj += 2) {
