@@ -419,6 +419,43 @@ static int execute_impl(gsk_ctx *ctx, int64_t first, int64_t count, int32_t *d_n
   if (ctx->prob.max_neighbors == 0) {
     rc = gsk_global_execute(ctx, first, count, d_nneigh, &launches);
     if (rc != GSK_OK) return rc;
+  } else if (!ctx->tg.is_grid && count > 0) {
+    // explicit points: process the slab in bin-sorted order (spatially coherent CTAs), then scatter back
+    const int k = ctx->prob.max_neighbors;
+    int *perm = nullptr, *nn_s = nullptr, *nbr_s = nullptr;
+    double *sx = nullptr, *sy = nullptr, *sz = nullptr, *ms = nullptr, *vs = nullptr;
+    if ((rc = gsk_points_sort(ctx, first, count, &perm, &sx, &sy, &sz)) != GSK_OK) return rc;
+    if ((rc = gsk_buf(ctx, BUF_PT_MEAN, sizeof(double) * (size_t)count, (void **)&ms)) != GSK_OK) return rc;
+    if ((rc = gsk_buf(ctx, BUF_PT_VAR, sizeof(double) * (size_t)count, (void **)&vs)) != GSK_OK) return rc;
+    if ((rc = gsk_buf(ctx, BUF_PT_NN, sizeof(int) * (size_t)count, (void **)&nn_s)) != GSK_OK) return rc;
+    if ((rc = gsk_buf(ctx, BUF_PT_NBR, sizeof(int) * (size_t)count * k, (void **)&nbr_s)) != GSK_OK) return rc;
+    const GskTargets tg_saved = ctx->tg;
+    const GskOut out_saved = ctx->out;
+    ctx->tg.pts[0] = sx; ctx->tg.pts[1] = sy; ctx->tg.pts[2] = sz;
+    ctx->tg.npts = count;
+    ctx->out = GskOut{};
+    ctx->out.n = 1;
+    ctx->out.mean[0] = ms;
+    ctx->out.var[0] = vs;
+    if (phase_timing) cudaEventRecord(ctx->ev[3], ctx->stream);
+    rc = gsk_launch_search(ctx, ctx->stream, 0, count, nn_s, nbr_s, &launches);
+    if (phase_timing) cudaEventRecord(ctx->ev[4], ctx->stream);
+    if (rc == GSK_OK) rc = gsk_launch_local_solve(ctx, ctx->stream, 0, count, nn_s, nbr_s, 0, &launches);
+    ctx->tg = tg_saved;
+    ctx->out = out_saved;
+    if (rc != GSK_OK) return rc;
+    if (phase_timing) {
+      cudaEventRecord(ctx->ev[5], ctx->stream);
+      cudaEventSynchronize(ctx->ev[5]);
+      float a = 0.f, b2 = 0.f;
+      cudaEventElapsedTime(&a, ctx->ev[3], ctx->ev[4]);
+      cudaEventElapsedTime(&b2, ctx->ev[4], ctx->ev[5]);
+      ms_search += a;
+      ms_solve += b2;
+    }
+    rc = gsk_points_unscatter(ctx, perm, count, ms, vs, ctx->out, nn_s, d_nneigh, nbr_s, d_neigh_idx, k);
+    if (rc != GSK_OK) return rc;
+    launches += 4;
   } else {
     const int k = ctx->prob.max_neighbors;
     // chunks of ~1M targets bound the neighbour-list scratch (4k+4 B per target); chunk edges are aligned

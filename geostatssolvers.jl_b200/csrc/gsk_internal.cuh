@@ -108,7 +108,8 @@ struct GlobalPlan;  // global.cu
 // gsk_plan / gsk_krige calls do not pay cudaMalloc/cudaFree (which synchronise the device)
 enum GskBufId {
   BUF_REC_ORIG, BUF_REC_SORTED, BUF_CELL_START, BUF_SUP, BUF_PTS0, BUF_PTS1, BUF_PTS2, BUF_CELL_OF, BUF_COUNTS,
-  BUF_G_A, BUF_G_X, BUF_G_DINV, BUF_G_E, BUF_G_YE, BUF_G_GEE, BUF_G_BM, BUF_G_PARTIAL, BUF_PEAK, BUF_COUNT
+  BUF_G_A, BUF_G_X, BUF_G_DINV, BUF_G_E, BUF_G_YE, BUF_G_GEE, BUF_G_BM, BUF_G_PARTIAL, BUF_PEAK,
+  BUF_PT_CELL, BUF_PT_COUNTS, BUF_PT_PERM, BUF_PT_X, BUF_PT_Y, BUF_PT_Z, BUF_PT_MEAN, BUF_PT_VAR, BUF_PT_NN, BUF_PT_NBR, BUF_COUNT
 };
 
 struct gsk_ctx {
@@ -175,6 +176,10 @@ int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long 
 int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const double *hz, const double *hv);
 int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, int *d_nn, int *launches);
 void gsk_global_free(gsk_ctx *ctx);
+// points.cu
+int gsk_points_sort(gsk_ctx *ctx, long long first, long long count, int **perm, double **sx, double **sy, double **sz);
+int gsk_points_unscatter(gsk_ctx *ctx, const int *perm, long long count, const double *ms, const double *vs,
+                         const GskOut &out, const int *nn_s, int *nn_out, const int *nbr_s, int *nbr_out, int k);
 // peak.cu
 int gsk_peak_measure(gsk_ctx *ctx, double *dfma, double *dmma);
 
