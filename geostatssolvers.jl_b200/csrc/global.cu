@@ -50,17 +50,24 @@ __global__ void assemble_kernel(GArgs g, double *__restrict__ A) {
   A[i + j * g.np] = v;
 }
 
-// ---- 64×64 tile product on the FP64 pipe: acc(4×4 per thread) += A(64×K)·B(K×64) ----
+// ---- 64×64 tile product on the FP64 tensor path (DMMA): acc += A(64×K)·B(K×64), K a multiple of 16 ----
 // A column-major (lda). B either column-major K×64 (TRANSB=false, element (k,n) at B[k + n·ldb])
 // or given as 64×K column-major to be used transposed (TRANSB=true, element (k,n) at B[n + k·ldb]).
+// 8 warps as 4 (M) × 2 (N); each warp owns a 16×32 sub-tile = 4 m16n8k16 accumulators: acc[n8][c] holds
+// element (row, col) = (wm·16 + g + 8·(c>>1), wn·32 + n8·8 + 2t + (c&1)), g = lane>>2, t = lane&3.
+constexpr int TLD = NB + 4;  // ≡ 4 (mod 16) doubles: conflict-free fragment loads
+__device__ __forceinline__ void acc_coords(int n8, int c, int &row, int &col) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  row = (warp >> 1) * 16 + (lane >> 2) + 8 * (c >> 1);
+  col = (warp & 1) * 32 + n8 * 8 + 2 * (lane & 3) + (c & 1);
+}
 template <bool TRANSB>
 __device__ __forceinline__ void tile_mma(const double *__restrict__ A, long long lda, const double *__restrict__ B,
-                                         long long ldb, int K, double (&acc)[4][4], double (*As)[NB + 1],
-                                         double (*Bs)[NB + 1]) {
-  const int tid = threadIdx.x;
-  const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
+                                         long long ldb, int K, double (&acc)[4][4], double (*As)[TLD],
+                                         double (*Bs)[TLD]) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, t = lane & 3;
   for (int k0 = 0; k0 < K; k0 += BK) {
-    // A tile: 64 rows × 16 k
     for (int e = tid; e < NB * BK; e += 256) {
       int m = e & 63, k = e >> 6;
       As[k][m] = A[m + (long long)(k0 + k) * lda];
@@ -77,17 +84,20 @@ __device__ __forceinline__ void tile_mma(const double *__restrict__ A, long long
       }
     }
     __syncthreads();
+    double af[8];
 #pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      double a[4], b[4];
+    for (int i = 0; i < 8; ++i) af[i] = As[t + 4 * (i >> 1)][wm * 16 + g + 8 * (i & 1)];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k][tm + i];
+    for (int n8 = 0; n8 < 4; ++n8) {
+      double bf[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tn + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < 4; ++i) bf[i] = Bs[t + 4 * i][wn * 32 + n8 * 8 + g];
+      asm volatile(
+          "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+          "{%12,%13,%14,%15}, {%0,%1,%2,%3};"
+          : "+d"(acc[n8][0]), "+d"(acc[n8][1]), "+d"(acc[n8][2]), "+d"(acc[n8][3])
+          : "d"(af[0]), "d"(af[1]), "d"(af[2]), "d"(af[3]), "d"(af[4]), "d"(af[5]), "d"(af[6]), "d"(af[7]),
+            "d"(bf[0]), "d"(bf[1]), "d"(bf[2]), "d"(bf[3]));
     }
     __syncthreads();
   }
@@ -136,25 +146,28 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double *__restrict__ A,
 // ---- panel below the diagonal block: P = A[i-block, j-block] · Dinvᵀ, in place ----
 __global__ void __launch_bounds__(256) trsm_panel_kernel(double *__restrict__ A, long long ld, long long j0,
                                                          const double *__restrict__ Dinv) {
-  __shared__ double As[BK][NB + 1];
-  __shared__ double Bs[BK][NB + 1];
+  __shared__ double As[BK][TLD];
+  __shared__ double Bs[BK][TLD];
   const long long i0 = j0 + NB + (long long)blockIdx.x * NB;
   double *blk = A + i0 + j0 * ld;
   double acc[4][4] = {};
   // the whole 64×64 source tile is consumed before anything is written back (same CTA owns it)
   tile_mma<true>(blk, ld, Dinv, NB, NB, acc, As, Bs);
-  const int tm = (threadIdx.x & 15) * 4, tn = (threadIdx.x >> 4) * 4;
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int n8 = 0; n8 < 4; ++n8)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) blk[(tm + i) + (long long)(tn + j) * ld] = acc[i][j];
+    for (int c = 0; c < 4; ++c) {
+      int row, col;
+      acc_coords(n8, c, row, col);
+      blk[row + (long long)col * ld] = acc[n8][c];
+    }
 }
 
 // ---- trailing update: A[bi, bj] −= P[bi]·P[bj]ᵀ for all tile pairs bi >= bj below the panel ----
 __global__ void __launch_bounds__(256) syrk_kernel(double *__restrict__ A, long long ld, long long j0, int nrem) {
-  __shared__ double As[BK][NB + 1];
-  __shared__ double Bs[BK][NB + 1];
+  __shared__ double As[BK][TLD];
+  __shared__ double Bs[BK][TLD];
   // linear index over the lower-triangular tile pairs
   int t = blockIdx.x;
   int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
@@ -165,12 +178,15 @@ __global__ void __launch_bounds__(256) syrk_kernel(double *__restrict__ A, long 
   const long long r0 = j0 + NB + (long long)bi * NB, c0 = j0 + NB + (long long)bj * NB;
   double acc[4][4] = {};
   tile_mma<true>(A + r0 + j0 * ld, ld, A + c0 + j0 * ld, ld, NB, acc, As, Bs);
-  const int tm = (threadIdx.x & 15) * 4, tn = (threadIdx.x >> 4) * 4;
   double *blk = A + r0 + c0 * ld;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int n8 = 0; n8 < 4; ++n8)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) blk[(tm + i) + (long long)(tn + j) * ld] -= acc[i][j];
+    for (int c = 0; c < 4; ++c) {
+      int row, col;
+      acc_coords(n8, c, row, col);
+      blk[row + (long long)col * ld] -= acc[n8][c];
+    }
 }
 
 // ---- Linv block row i:  X[i, jb] = −Dinv_i · Σ_{m=jb}^{i−1} L[i, m]·X[m, jb]  (jb < i);  X[i,i] = Dinv_i ----
@@ -178,8 +194,8 @@ __global__ void __launch_bounds__(256) linv_row_kernel(const double *__restrict_
                                                        long long ld, int bi, const double *__restrict__ Dinv_all) {
   // As/Bs are only live inside tile_mma; T reuses the same shared memory afterwards
   __shared__ double buf[NB * (NB + 1)];
-  double (*As)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(buf);
-  double (*Bs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(buf + BK * (NB + 1));
+  double (*As)[TLD] = reinterpret_cast<double (*)[TLD]>(buf);
+  double (*Bs)[TLD] = reinterpret_cast<double (*)[TLD]>(buf + BK * TLD);
   double (*T)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(buf);
   const int jb = blockIdx.x;
   const long long i0 = (long long)bi * NB, j0 = (long long)jb * NB;
@@ -196,9 +212,13 @@ __global__ void __launch_bounds__(256) linv_row_kernel(const double *__restrict_
   double acc[4][4] = {};
   tile_mma<false>(A + i0 + j0 * ld, ld, X + j0 + j0 * ld, ld, (bi - jb) * NB, acc, As, Bs);
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int n8 = 0; n8 < 4; ++n8)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) T[tm + i][tn + j] = acc[i][j];
+    for (int c = 0; c < 4; ++c) {
+      int row, col;
+      acc_coords(n8, c, row, col);
+      T[row][col] = acc[n8][c];
+    }
   __syncthreads();
   // out = −Di · T   (Di lower triangular 64×64)
 #pragma unroll
