@@ -66,7 +66,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(device)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+                                          "-lms", "50", "-i", str(device)], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
@@ -147,7 +147,7 @@ def workload_name(cfg, spec):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3a", "C3b", "C4", "C5"])
@@ -359,10 +359,10 @@ def main():
             sl = spec.with_slab((T1 - sample) // 2, sample)
             O.krige(sl)
             best = 1e30
-            for _ in range(3):
+            for _ in range(5):
                 c0 = time.perf_counter(); O.krige(sl); best = min(best, time.perf_counter() - c0)
             line["cpu_baseline"] = {"value": sample / best, "unit": UNIT, "cores": O.threads(), "kind": "port",
-                                    "sample": f"{sample} consecutive targets of the grid, best of 3 (C oracle, KD-tree, OpenMP all cores)"}
+                                    "sample": f"{sample} consecutive targets of the grid, best of 5 passes (C oracle, KD-tree, OpenMP all cores)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
