@@ -154,6 +154,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="targets per step of the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--targets", type=int, default=0, help="limit the per-rank slab (debug)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: per-GPU work fixed (grid and samples grow with N, default); strong: the named config's grid is sharded over N")
     ap.add_argument("--gather", default="multicast", choices=["peer", "multicast", "nccl"],
                     help="N>1 result gather: stores into every rank's symmetric-memory buffer fused in the solve kernel "
                          "(peer), the same through one NVLS multicast store (multicast), or an NCCL all-gather (nccl)")
@@ -178,7 +180,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    spec = weak_spec(gskrige, args.config, world)
+    spec = weak_spec(gskrige, args.config, world if args.scaling == "weak" else 1)
     T = spec.n_targets
     first, count = gskrige.slab_bounds(T, rank, world)
     if args.targets:
@@ -317,7 +319,8 @@ def main():
         extra = {}
         if k:
             achieved = flops_t * count / (solve_ms * 1e-3) / 1e12          # all solve launches of a step together
-            kernel, bound, peak, frac = "local_solve_kernel", "fp64", dfma, achieved / dfma
+            kernel = "local_solve_small_kernel" if (k <= 20 and spec.params["estimator"] != 2) else "local_solve_kernel"
+            bound, peak, frac = "fp64", dfma, achieved / dfma
         else:
             # global path: the Gram formulation needs only the forward triangular solve, i.e. n² flop per target
             # instead of the canonical 2(n+c)² — both are reported; frac uses the EXECUTED flops (conservative)
@@ -335,7 +338,7 @@ def main():
             traffic = json.loads(tf.read_text()).get(args.config)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.config, spec), "targets_per_gpu": count, "l2": "flushed between timed steps (256 MB write)",
                        "multi_gpu": ("slabs of the slowest axis, samples replicated; " + gather_mode) if world > 1 else "single GPU"},

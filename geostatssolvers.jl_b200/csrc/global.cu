@@ -103,6 +103,69 @@ __device__ __forceinline__ void tile_mma(const double *__restrict__ A, long long
   }
 }
 
+// ---- pipelined variant for long K (Linv rows): 3-stage cp.async ring, NN operands ----
+constexpr int LS = 3;
+constexpr int LA_STAGE = BK * TLD;    // A stage: [k][m], m contiguous
+constexpr int LB_LD = BK + 4;         // B stage: [n][k], k contiguous; ≡ 4 (mod 16) doubles
+constexpr int LB_STAGE = NB * LB_LD;
+constexpr size_t LINV_SMEM = sizeof(double) * (size_t)LS * (LA_STAGE + LB_STAGE);
+__device__ __forceinline__ void cp16(void *dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src));
+}
+__device__ __forceinline__ void tile_mma_nn_async(const double *__restrict__ A, long long lda,
+                                                  const double *__restrict__ B, long long ldb, int K,
+                                                  double (&acc)[4][4], double *sm) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, t = lane & 3;
+  const int nk = K / BK;
+  auto load = [&](int s, int kt) {
+    double *as = sm + (size_t)s * LA_STAGE;
+    double *bs = sm + (size_t)LS * LA_STAGE + (size_t)s * LB_STAGE;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = tid + 256 * i;
+      const int k = c >> 5, mc = c & 31;
+      cp16(as + k * TLD + 2 * mc, A + 2 * mc + (long long)(kt * BK + k) * lda);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = tid + 256 * i;
+      const int n = c >> 3, kc = c & 7;
+      cp16(bs + n * LB_LD + 2 * kc, B + kt * BK + 2 * kc + (long long)n * ldb);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < LS - 1; ++s) {
+    if (s < nk) load(s, s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(LS - 2) : "memory");
+    __syncthreads();
+    if (kt + LS - 1 < nk) load((kt + LS - 1) % LS, kt + LS - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const double *as = sm + (size_t)(kt % LS) * LA_STAGE;
+    const double *bs = sm + (size_t)LS * LA_STAGE + (size_t)(kt % LS) * LB_STAGE;
+    double af[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) af[i] = as[(t + 4 * (i >> 1)) * TLD + wm * 16 + g + 8 * (i & 1)];
+#pragma unroll
+    for (int n8 = 0; n8 < 4; ++n8) {
+      double bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bf[i] = bs[(wn * 32 + n8 * 8 + g) * LB_LD + t + 4 * i];
+      asm volatile(
+          "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+          "{%12,%13,%14,%15}, {%0,%1,%2,%3};"
+          : "+d"(acc[n8][0]), "+d"(acc[n8][1]), "+d"(acc[n8][2]), "+d"(acc[n8][3])
+          : "d"(af[0]), "d"(af[1]), "d"(af[2]), "d"(af[3]), "d"(af[4]), "d"(af[5]), "d"(af[6]), "d"(af[7]),
+            "d"(bf[0]), "d"(bf[1]), "d"(bf[2]), "d"(bf[3]));
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+}
+
 // ---- diagonal block: Cholesky of A[j0:j0+64, j0:j0+64] in place, and its inverse into Dinv ----
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double *__restrict__ A, long long ld, long long j0,
                                                          double *__restrict__ Dinv) {
@@ -192,11 +255,10 @@ __global__ void __launch_bounds__(256) syrk_kernel(double *__restrict__ A, long 
 // ---- Linv block row i:  X[i, jb] = −Dinv_i · Σ_{m=jb}^{i−1} L[i, m]·X[m, jb]  (jb < i);  X[i,i] = Dinv_i ----
 __global__ void __launch_bounds__(256) linv_row_kernel(const double *__restrict__ A, double *__restrict__ X,
                                                        long long ld, int bi, const double *__restrict__ Dinv_all) {
-  // As/Bs are only live inside tile_mma; T reuses the same shared memory afterwards
-  __shared__ double buf[NB * (NB + 1)];
-  double (*As)[TLD] = reinterpret_cast<double (*)[TLD]>(buf);
-  double (*Bs)[TLD] = reinterpret_cast<double (*)[TLD]>(buf + BK * TLD);
-  double (*T)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(buf);
+  // the stage ring is only live inside tile_mma_nn_async; T reuses the same shared memory afterwards
+  extern __shared__ __align__(16) double lbuf[];
+  static_assert(LINV_SMEM >= sizeof(double) * NB * (NB + 1), "T must fit in the stage ring");
+  double (*T)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(lbuf);
   const int jb = blockIdx.x;
   const long long i0 = (long long)bi * NB, j0 = (long long)jb * NB;
   const double *Di = Dinv_all + (size_t)bi * NB * NB;
@@ -210,7 +272,7 @@ __global__ void __launch_bounds__(256) linv_row_kernel(const double *__restrict_
     return;
   }
   double acc[4][4] = {};
-  tile_mma<false>(A + i0 + j0 * ld, ld, X + j0 + j0 * ld, ld, (bi - jb) * NB, acc, As, Bs);
+  tile_mma_nn_async(A + i0 + j0 * ld, ld, X + j0 + j0 * ld, ld, (bi - jb) * NB, acc, lbuf);
 #pragma unroll
   for (int n8 = 0; n8 < 4; ++n8)
 #pragma unroll
@@ -591,7 +653,8 @@ int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const doub
     }
   }
   // Linv, block row by block row
-  for (int bi = 0; bi < nblk; ++bi) linv_row_kernel<<<bi + 1, 256, 0, st>>>(g->A, g->X, np, bi, g->Dinv);
+  GSK_CUDA_CHECK(ctx, cudaFuncSetAttribute(linv_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LINV_SMEM));
+  for (int bi = 0; bi < nblk; ++bi) linv_row_kernel<<<bi + 1, 256, LINV_SMEM, st>>>(g->A, g->X, np, bi, g->Dinv);
   // E, Y_E, G_EE
   build_e_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(ga, ctx->es, g->E);
   linv_times_e_kernel<<<(unsigned)((np + 7) / 8), 256, 0, st>>>(g->X, np, np, g->E, g->ne, g->YE);
