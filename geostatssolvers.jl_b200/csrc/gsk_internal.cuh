@@ -95,6 +95,7 @@ struct GskSearchArgs {
   long long t0[3];
   int ntile[3];
   int margin0[3];  // initial block margin in bins
+  int scap;        // staged records per chunk
   int *nn;         // out: neighbours per target
   int *nbr;        // out: count × k original indices sorted by (d², idx), −1 padded
 };

@@ -14,6 +14,7 @@
 // round-to-nearest mul/add and no FMA — the oracle's chain — so neighbour sets are bit-identical
 // and ties fall to the lower sample index (north_star).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -22,7 +23,7 @@
 namespace {
 
 constexpr int NT = 128;       // targets (threads) per CTA
-constexpr int SCAP = 1024;    // staged records per chunk (32 KB)
+constexpr int SCAP_MAX = 1024;  // upper bound of staged records per chunk (32 KB)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -86,6 +87,7 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
   static_assert(TX * TY * TZ == NT, "tile must hold NT targets");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = a.k;
+  const int SCAP = a.scap;
   double4 *stage = reinterpret_cast<double4 *>(smem_raw);                 // SCAP records
   double *topd = reinterpret_cast<double *>(smem_raw + sizeof(double4) * SCAP);  // [K][NT]
   int *topi = reinterpret_cast<int *>(topd + (size_t)K * NT);             // [K][NT]
@@ -334,7 +336,26 @@ int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long 
   a.nn = d_nn;
   a.nbr = d_nbr;
   for (int d = 0; d < 3; ++d) a.margin0[d] = ctx->margin0[d];
-  const size_t smem = sizeof(double4) * SCAP + (size_t)a.k * NT * (sizeof(double) + sizeof(int));
+  {
+    // staging capacity: just enough for the block a tile is expected to scan (smaller shared-memory footprint
+    // → more resident CTAs, which is what the latency-bound insertion loop needs); larger blocks are simply
+    // processed in several chunks. GSK_SCAP overrides (development tunable).
+    static const int scap_env = getenv("GSK_SCAP") ? atoi(getenv("GSK_SCAP")) : 0;
+    double expect = 512.0;
+    const int dim = ctx->tg.dim;
+    if (ctx->tg.is_grid && ctx->bins.ncells > 0) {
+      const int tdim[3] = {dim == 1 ? NT : (dim == 2 ? 16 : 8), dim == 1 ? 1 : (dim == 2 ? 8 : 4), dim == 3 ? 4 : 1};
+      double nb = 1.0;
+      for (int d = 0; d < dim; ++d)
+        nb *= std::min((double)ctx->bins.nb[d],
+                       tdim[d] * fabs(ctx->tg.gsp[d]) / ctx->bins.cell[d] + 1.0 + 2.0 * ctx->margin0[d]);
+      expect = nb * (double)ctx->prob.n_samples / (double)ctx->bins.ncells;
+    }
+    int sc = 128;
+    while (sc < SCAP_MAX && sc < 1.25 * expect) sc *= 2;
+    a.scap = scap_env > 0 ? std::min(scap_env, SCAP_MAX) : sc;
+  }
+  const size_t smem = sizeof(double4) * a.scap + (size_t)a.k * NT * (sizeof(double) + sizeof(int));
   const int dim = ctx->tg.dim;
   unsigned nblocks;
   int tile[3] = {NT, 1, 1};
