@@ -317,3 +317,36 @@ def test_unordered_point_targets_are_bin_sorted(gsk, ctx, oracle):
     assert_parity(mean, var, om, ov, scale=2.0)
     m2, v2 = ctx.krige(spec.with_slab(150_000, 12_345))
     assert np.array_equal(m2, mean[150_000:162_345]) and np.array_equal(v2, var[150_000:162_345])
+
+
+def test_more_edge_shapes(gsk, ctx, oracle):
+    """Non-unit spacing with a negative origin (block support scales with the cell), k at the library maximum
+    (one warp per target configuration), every target missing (min_neighbors > what the ball can hold), and a
+    slab that starts and ends in the middle of grid rows."""
+    rng = np.random.default_rng(21)
+    # 1) anisotropic spacing, negative origin
+    coords = [rng.uniform(-50, 30, 700), rng.uniform(10, 90, 700)]
+    vals = np.sin(coords[0] / 11.0) * np.cos(coords[1] / 7.0)
+    spacing = [2.0, 0.5]
+    spec = gsk.ProblemSpec(coords=coords, values=vals, grid_dims=(40, 160), grid_origin=(-50.0, 10.0), grid_spacing=spacing,
+                           support=gsk.default_support_py(spacing, 12.0), vario_kind=gsk.VARIO_EXPONENTIAL,
+                           vario_range=12.0, vario_nugget=0.1, max_neighbors=14)
+    _check(gsk, ctx, oracle, spec)
+    # 2) k = 96 (GSK_MAX_NEIGHBORS), Ordinary and Universal degree 2 (e = 12 extra rows)
+    c3, v3 = gsk.synth.make_samples(55, 4000, (30, 30, 30))
+    for est, deg in ((gsk.EST_ORDINARY, 0), (gsk.EST_UNIVERSAL, 2)):
+        big = gsk.ProblemSpec(coords=c3, values=v3, grid_dims=(12, 12, 12), grid_origin=(9.0, 9.0, 9.0),
+                              support=gsk.default_support_py([1.0] * 3, 8.0), vario_kind=gsk.VARIO_SPHERICAL,
+                              vario_range=8.0, vario_nugget=0.05, estimator=est, uk_degree=deg, max_neighbors=96)
+        _check(gsk, ctx, oracle, big, **(dict(atol_mean=1e-6, atol_var=1e-6) if deg == 2 else {}))
+    # 3) everything missing
+    none = gsk.synth.config_spec("C2", scale=0.1, ball_radius=0.5, min_neighbors=5)
+    mean, var, nn, idx = ctx.krige(none, want_neighbors=True)
+    assert np.isnan(mean).all() and np.isnan(var).all() and nn.max() < 5
+    om, ov, onn, oidx = oracle.krige(none, want_neighbors=True)
+    assert np.array_equal(nn, onn) and np.array_equal(idx, oidx)
+    # 4) slab cutting through rows
+    base = gsk.synth.config_spec("C3b", scale=0.12)
+    full = ctx.krige(base)
+    cut = ctx.krige(base.with_slab(1234, 5677))
+    assert np.array_equal(cut[0], full[0][1234:1234 + 5677]) and np.array_equal(cut[1], full[1][1234:1234 + 5677])
