@@ -580,14 +580,37 @@ extern "C" GSK_API int gsk_krige(gsk_ctx *ctx, const gsk_problem *p, double *mea
     if (rc != GSK_OK) return rc;
     d_idx = ctx->d_nbr;
   }
-  rc = gsk_execute(ctx, first, count, d_mean, d_var, d_nn, d_idx);
-  if (rc != GSK_OK) return rc;
-  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(mean_out, d_mean, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
-  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(var_out, d_var, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
-  if (d_nn)
-    GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(nneigh_out, d_nn, sizeof(int) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
-  if (d_idx)
-    GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(neigh_idx_out, d_idx, sizeof(int) * (size_t)count * k, cudaMemcpyDeviceToHost, ctx->stream));
+  // The slab is computed in a few pieces; the device→host copies of a finished piece run on the side stream
+  // while the next piece is being computed (they overlap only when the host buffers are page-locked).
+  {
+    long long piece = count;
+    if (count >= (1ll << 19)) {
+      piece = (count + 3) / 4;
+      if (ctx->tg.is_grid) {
+        const int dim = ctx->tg.dim;
+        const long long unit = (dim == 3) ? ctx->tg.gdim[0] * ctx->tg.gdim[1] * 4 : (dim == 2 ? ctx->tg.gdim[0] * 8 : 128);
+        if (unit <= piece) piece = (piece + unit - 1) / unit * unit;
+      }
+    }
+    int pi = 0;
+    for (long long off = 0; off < count; off += piece, ++pi) {
+      const long long cnt = std::min<long long>(piece, count - off);
+      rc = gsk_execute(ctx, first + off, cnt, d_mean + off, d_var + off, d_nn ? d_nn + off : nullptr,
+                       d_idx ? d_idx + off * k : nullptr);
+      if (rc != GSK_OK) return rc;
+      const int eb = pi & 1;
+      GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_search[eb], ctx->stream));  // reused as a "piece done" marker
+      GSK_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_search[eb], 0));
+      GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(mean_out + off, d_mean + off, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2));
+      GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(var_out + off, d_var + off, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2));
+      if (d_nn)
+        GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(nneigh_out + off, d_nn + off, sizeof(int) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2));
+      if (d_idx)
+        GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(neigh_idx_out + off * k, d_idx + off * k, sizeof(int) * (size_t)cnt * k, cudaMemcpyDeviceToHost, ctx->stream2));
+    }
+    ctx->timing.targets = count;
+  }
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream2));
   GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   GSK_CUDA_CHECK(ctx, cudaGetLastError());
   return GSK_OK;
