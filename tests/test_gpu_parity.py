@@ -350,3 +350,28 @@ def test_more_edge_shapes(gsk, ctx, oracle):
     full = ctx.krige(base)
     cut = ctx.krige(base.with_slab(1234, 5677))
     assert np.array_equal(cut[0], full[0][1234:1234 + 5677]) and np.array_equal(cut[1], full[1][1234:1234 + 5677])
+
+
+def test_execute_peers_stores_into_every_destination(gsk, ctx):
+    """gsk_execute_peers (the fused result gather): with three destination buffers standing in for three ranks'
+    symmetric-memory buffers, every buffer receives the slab at out_offset; local and global paths."""
+    import torch
+    for name, kw in (("C2", dict(scale=0.15)), ("C1", dict(grid=(30, 30), n=200))):
+        spec = gsk.synth.config_spec(name, **kw)
+        T = spec.n_targets
+        first, count = T // 3, T // 2
+        ref_m, ref_v = ctx.krige(spec.with_slab(first, count))
+        own = gsk.Context(0)
+        own.set_stream(torch.cuda.current_stream().cuda_stream)
+        own.plan(spec)
+        bufs = [torch.full((2, T), -7.0, dtype=torch.float64, device="cuda") for _ in range(3)]
+        own.execute_peers(first, count, [b[0].data_ptr() for b in bufs], [b[1].data_ptr() for b in bufs],
+                          out_offset=first)
+        torch.cuda.synchronize()
+        for b in bufs:
+            got = b.cpu().numpy()
+            assert np.array_equal(got[0, first:first + count], ref_m) and np.array_equal(got[1, first:first + count], ref_v)
+            assert np.all(got[:, :first] == -7.0) and np.all(got[:, first + count:] == -7.0)
+        with pytest.raises(gsk.GskError):
+            own.execute_peers(first, count, [bufs[0][0].data_ptr()] * 9, [bufs[0][1].data_ptr()] * 9)
+        own.close()
