@@ -146,8 +146,16 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
   constexpr int TPW = 32 / G;
   constexpr int TPC = TPW * (CTA_THREADS / 32);
   constexpr bool UNROLL_P = (G == 4);  // small systems: unroll the left-looking loops completely
-  // register row r·G + l exists in storage (static except in the last, partially covered slot)
-#define GSK_ROW_OK(r) (((r) * G + G <= RS) || ((r) * G + l < RS))
+  // Rows are dealt to the register slots bottom-up: slot r holds rows ROW0(r) + l, ROW0(r) = RS − G·(r+1)
+  // (the top slot may start below zero; those rows do not exist). For a panel starting at column c0 the live
+  // rows [c0, RS) then fill ceil((RS − c0)/G) slots exactly — with a top-down deal and G = 32 most lanes of the
+  // upper slots would be dead rows.
+  // When RS is a multiple of G both deals are equivalent and the plain top-down one is kept.
+  constexpr bool BOTTOM_UP = (RS % G) != 0;
+#define ROW0(r) (BOTTOM_UP ? RS - G * ((r) + 1) : (r) * G)
+#define GSK_ROW_OK(r) ((ROW0(r) >= 0) || (ROW0(r) + l >= 0))
+#define SLOT_LIVE(r, c) (ROW0(r) + G - 1 >= (c))          /* slot r still holds rows >= c */
+#define OWNER_SLOT(j) (BOTTOM_UP ? (RS - 1 - (j)) / G : (j) / G)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sm = reinterpret_cast<double *>(smem_raw);
   double *sup = sm;  // [3][nsup]
@@ -274,12 +282,12 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
   // ---- phase 3: covariance block in place. Lane l owns rows i = r·G + l (coordinates in registers) and
   //      walks the columns p; the R evaluations per column are independent ----
   {
-    constexpr int RS_S = (KCMAX + G - 1) / G;  // slots that can hold neighbour rows
+    constexpr int RS_S = R;  // every slot may hold neighbour rows
     double xi[RS_S], yi[RS_S], zi[RS_S];
 #pragma unroll
     for (int r = 0; r < RS_S; ++r) {
-      const int i = r * G + l;
-      const bool ok = i < KC;
+      const int i = ROW0(r) + l;
+      const bool ok = i >= 0 && i < KC;
       xi[r] = ok ? nbX[i] : 0.0;
       yi[r] = ok ? nbY[i] : 0.0;
       zi[r] = (DIM == 3 && ok) ? nbZ[i] : 0.0;
@@ -288,7 +296,6 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
 #pragma unroll
     for (int sb = 0; sb < KCMAX; sb += A) {
       if (sb < KC) {
-        const int rlo = sb / G;
         for (int pp = 0; pp < A; ++pp) {
           const int p = sb + pp;
           const bool valid_p = p < nn;
@@ -296,8 +303,8 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
           double *col = S + col_off<RT, A>(sb) + pp * (RT - sb) - sb + l;
 #pragma unroll
           for (int r = 0; r < RS_S; ++r) {
-            if (r >= rlo) {  // static after unrolling
-              const int i = r * G + l;
+            if (SLOT_LIVE(r, sb) && ROW0(r) < KCMAX) {  // static after unrolling; slots of pure extra rows are skipped
+              const int i = ROW0(r) + l;
               const double dx = xi[r] - xp, dy = yi[r] - yp;
               double d2 = fma(dy, dy, dx * dx);
               if (DIM == 3) {
@@ -307,7 +314,7 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
               double v = cov_fast<VK>(vg, d2);
               v = (i > p && i < nn) ? v : 0.0;
               v = (i == p) ? (valid_p ? vg.sill : 1.0) : v;
-              if (i >= sb && i < KC) col[r * G] = v;
+              if (i >= sb && i < KC) col[ROW0(r)] = v;
             }
           }
         }
@@ -322,16 +329,15 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
 #pragma unroll
   for (int c0 = 0; c0 < KCMAX; c0 += W) {
     if (c0 < KC) {
-      const int rmin = c0 / G;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        if (r >= rmin) {
+        if (SLOT_LIVE(r, c0)) {
 #pragma unroll
           for (int jj = 0; jj < W; ++jj) {
             const int j = c0 + jj;
             const int sj = j & ~(A - 1);
-            const bool in = ((r * G >= sj) || (r * G + l >= sj)) && GSK_ROW_OK(r);
-            acc[r][jj] = in ? Sl[col_off<RT, A>(j) - sj + r * G] : 0.0;
+            const bool in = (ROW0(r) >= sj) || (ROW0(r) + l >= sj);
+            acc[r][jj] = in ? Sl[col_off<RT, A>(j) - sj + ROW0(r)] : 0.0;
           }
         }
       }
@@ -347,8 +353,8 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (r >= rmin) {
-            const double own = GSK_ROW_OK(r) ? col[r * G + l] : 0.0;
+          if (SLOT_LIVE(r, c0)) {
+            const double own = GSK_ROW_OK(r) ? col[ROW0(r) + l] : 0.0;
 #pragma unroll
             for (int jj = 0; jj < W; ++jj) acc[r][jj] = fma(-own, piv[jj], acc[r][jj]);
           }
@@ -371,8 +377,8 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
           }
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            if (r >= rmin) {
-              const double own = GSK_ROW_OK(r) ? colp[r * G + l] : 0.0;
+            if (SLOT_LIVE(r, c0)) {
+              const double own = GSK_ROW_OK(r) ? colp[ROW0(r) + l] : 0.0;
 #pragma unroll
               for (int jj = 0; jj < W; ++jj) acc[r][jj] = fma(-own, piv[jj], acc[r][jj]);
             }
@@ -385,23 +391,23 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
       for (int jj = 0; jj < W; ++jj) {
         const int j = c0 + jj;
         const int sj = j & ~(A - 1);
-        const int ro = j / G, lo = j % G;  // owner of row j
+        const int ro = OWNER_SLOT(j), lo = j - ROW0(ro);  // owner of row j
         const double d = __shfl_sync(0xffffffffu, acc[ro][jj], gbase + lo);
         const double rinv = gsk_rsqrt(d);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (r >= rmin) {
+          if (SLOT_LIVE(r, c0)) {
             acc[r][jj] *= rinv;
-            if ((r * G >= j || r * G + l >= j) && GSK_ROW_OK(r)) Sl[col_off<RT, A>(j) - sj + r * G] = acc[r][jj];
+            if (ROW0(r) >= j || ROW0(r) + l >= j) Sl[col_off<RT, A>(j) - sj + ROW0(r)] = acc[r][jj];
           }
         }
 #pragma unroll
         for (int j2 = jj + 1; j2 < W; ++j2) {
-          const int r2 = (c0 + j2) / G, l2 = (c0 + j2) % G;  // owner of row c0 + j2
+          const int r2 = OWNER_SLOT(c0 + j2), l2 = (c0 + j2) - ROW0(r2);  // owner of row c0 + j2
           const double lj = __shfl_sync(0xffffffffu, acc[r2][jj], gbase + l2);
 #pragma unroll
           for (int r = 0; r < R; ++r)
-            if (r >= rmin) acc[r][j2] = fma(-acc[r][jj], lj, acc[r][j2]);
+            if (SLOT_LIVE(r, c0)) acc[r][j2] = fma(-acc[r][jj], lj, acc[r][j2]);
         }
       }
       __syncwarp();
@@ -412,11 +418,11 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
   for (int cc = 0; cc < EPr; cc += W) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      if (r * G + G > KC && r * G < KC + EPr) {  // slot holds extra rows (warp-uniform)
+      if (ROW0(r) + G > KC && ROW0(r) < KC + EPr) {  // slot holds extra rows (warp-uniform)
         double g[W];
 #pragma unroll
         for (int jj = 0; jj < W; ++jj) g[jj] = 0.0;
-        const int i = r * G + l;
+        const int i = ROW0(r) + l;
         const bool mine = i >= KC && i < KC + EPr;
         const double *col = S;
 #pragma unroll 4
@@ -502,6 +508,9 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
     gsk_store_result(a.out, t, mean, var);
   }
 #undef GSK_ROW_OK
+#undef ROW0
+#undef SLOT_LIVE
+#undef OWNER_SLOT
 }
 
 template <int G, int R, int W, int RS, int NT, int DIM, int VK>
