@@ -82,7 +82,10 @@ __device__ __forceinline__ int block_excl_scan(int v, int *warp_buf, int *total)
   return base + incl - v;
 }
 
-template <int TX, int TY, int TZ, int DIM>
+// HEAP selects how a thread keeps its k best candidates: an ascending list with insertion (cheap for small k,
+// O(k) per accepted candidate) or a binary max-heap (O(log k) per accepted candidate, heap-sorted once at the
+// end) for large k.
+template <int TX, int TY, int TZ, int DIM, bool HEAP>
 __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
   static_assert(TX * TY * TZ == NT, "tile must hold NT targets");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -249,24 +252,71 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
             if (d2 > worst) continue;
             const int oi = (int)__double_as_longlong(rc.w);
             if (d2 == worst && oi > worst_i) continue;
-            int p = (cnt < K) ? cnt : K - 1;
-            while (p > 0) {
-              double dp = topd[(size_t)(p - 1) * NT + tid];
-              int ip = topi[(size_t)(p - 1) * NT + tid];
-              if (d2 < dp || (d2 == dp && oi < ip)) {
-                topd[(size_t)p * NT + tid] = dp;
-                topi[(size_t)p * NT + tid] = ip;
-                --p;
-              } else {
-                break;
+#define TD(sl) topd[(size_t)(sl) * NT + tid]
+#define TI(sl) topi[(size_t)(sl) * NT + tid]
+            if (!HEAP) {
+              int p = (cnt < K) ? cnt : K - 1;
+              while (p > 0) {
+                double dp = TD(p - 1);
+                int ip = TI(p - 1);
+                if (d2 < dp || (d2 == dp && oi < ip)) {
+                  TD(p) = dp;
+                  TI(p) = ip;
+                  --p;
+                } else {
+                  break;
+                }
               }
-            }
-            topd[(size_t)p * NT + tid] = d2;
-            topi[(size_t)p * NT + tid] = oi;
-            if (cnt < K) ++cnt;
-            if (cnt == K) {
-              worst = topd[(size_t)(K - 1) * NT + tid];
-              worst_i = topi[(size_t)(K - 1) * NT + tid];
+              TD(p) = d2;
+              TI(p) = oi;
+              if (cnt < K) ++cnt;
+              if (cnt == K) {
+                worst = TD(K - 1);
+                worst_i = TI(K - 1);
+              }
+            } else {
+              int i;
+              if (cnt < K) {  // sift up
+                i = cnt++;
+                while (i > 0) {
+                  const int par = (i - 1) >> 1;
+                  const double dp = TD(par);
+                  const int ip = TI(par);
+                  if (d2 > dp || (d2 == dp && oi > ip)) {
+                    TD(i) = dp;
+                    TI(i) = ip;
+                    i = par;
+                  } else {
+                    break;
+                  }
+                }
+              } else {  // replace the root (the current k-th best), sift down
+                i = 0;
+                for (;;) {
+                  int c = 2 * i + 1;
+                  if (c >= K) break;
+                  double dc = TD(c);
+                  int ic = TI(c);
+                  if (c + 1 < K) {
+                    const double dr = TD(c + 1);
+                    const int ir = TI(c + 1);
+                    if (dr > dc || (dr == dc && ir > ic)) { dc = dr; ic = ir; ++c; }
+                  }
+                  if (dc > d2 || (dc == d2 && ic > oi)) {
+                    TD(i) = dc;
+                    TI(i) = ic;
+                    i = c;
+                  } else {
+                    break;
+                  }
+                }
+              }
+              TD(i) = d2;
+              TI(i) = oi;
+              if (cnt == K) {
+                worst = TD(0);
+                worst_i = TI(0);
+              }
             }
           }
         }
@@ -309,6 +359,35 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
 
   // ---- emit: ascending (d², idx); ball search keeps sqrt(d²) <= radius (inclusive) ----
   if (active) {
+    if (HEAP) {  // heap sort in place: repeatedly move the maximum behind the shrinking heap
+      for (int end = cnt - 1; end > 0; --end) {
+        const double kd = TD(end);
+        const int ki = TI(end);
+        TD(end) = TD(0);
+        TI(end) = TI(0);
+        int i = 0;
+        for (;;) {
+          int c = 2 * i + 1;
+          if (c >= end) break;
+          double dc = TD(c);
+          int ic = TI(c);
+          if (c + 1 < end) {
+            const double dr = TD(c + 1);
+            const int ir = TI(c + 1);
+            if (dr > dc || (dr == dc && ir > ic)) { dc = dr; ic = ir; ++c; }
+          }
+          if (dc > kd || (dc == kd && ic > ki)) {
+            TD(i) = dc;
+            TI(i) = ic;
+            i = c;
+          } else {
+            break;
+          }
+        }
+        TD(i) = kd;
+        TI(i) = ki;
+      }
+    }
     int nn = cnt;
     if (a.use_ball) {
       nn = 0;
@@ -319,6 +398,8 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
     int *out = a.nbr + t * K;
     for (int i = 0; i < K; ++i) out[i] = (i < nn) ? topi[(size_t)i * NT + tid] : -1;
   }
+#undef TD
+#undef TI
 }
 
 }  // namespace
@@ -387,16 +468,21 @@ int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long 
     nblocks = (unsigned)((count + NT - 1) / NT);
   }
   cudaError_t e;
+  static const int heap_min_k = getenv("GSK_HEAP_MIN_K") ? atoi(getenv("GSK_HEAP_MIN_K")) : 24;  // development tunable
+  const bool heap = a.k >= heap_min_k;
+#define GSK_LAUNCH_SEARCH(TX, TY, TZ, D, H)                                                                        \
+  do {                                                                                                             \
+    e = cudaFuncSetAttribute(search_kernel<TX, TY, TZ, D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e == cudaSuccess) search_kernel<TX, TY, TZ, D, H><<<nblocks, NT, smem, st>>>(a);                           \
+  } while (0)
   if (dim == 1) {
-    e = cudaFuncSetAttribute(search_kernel<NT, 1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) search_kernel<NT, 1, 1, 1><<<nblocks, NT, smem, st>>>(a);
+    if (heap) GSK_LAUNCH_SEARCH(NT, 1, 1, 1, true); else GSK_LAUNCH_SEARCH(NT, 1, 1, 1, false);
   } else if (dim == 2) {
-    e = cudaFuncSetAttribute(search_kernel<16, 8, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) search_kernel<16, 8, 1, 2><<<nblocks, NT, smem, st>>>(a);
+    if (heap) GSK_LAUNCH_SEARCH(16, 8, 1, 2, true); else GSK_LAUNCH_SEARCH(16, 8, 1, 2, false);
   } else {
-    e = cudaFuncSetAttribute(search_kernel<8, 4, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) search_kernel<8, 4, 4, 3><<<nblocks, NT, smem, st>>>(a);
+    if (heap) GSK_LAUNCH_SEARCH(8, 4, 4, 3, true); else GSK_LAUNCH_SEARCH(8, 4, 4, 3, false);
   }
+#undef GSK_LAUNCH_SEARCH
   GSK_CUDA_CHECK(ctx, e);
   GSK_CUDA_CHECK(ctx, cudaGetLastError());
   if (launches) *launches += 1;
