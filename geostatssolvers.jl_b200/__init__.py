@@ -7,7 +7,7 @@ Only the Kriging hot path exists here: the host mirror of the re
 interface (host.py), the ctypes binding of the C ABI (_abi.py), the build recipe (build.py)
 and the CUDA sources (csrc/). No CPU fallback.
 """
-from ._abi import (Context, GskError, ProblemSpec, default_support, default_support_py, load_library,  # noqa: F401
+from ._abi import (Context, GskError, ProblemSpec, krige_multi, default_support, default_support_py, load_library,  # noqa: F401
                    uk_exponents, EXPORTED_SYMBOLS, LIB_PATH,
                    VARIO_GAUSSIAN, VARIO_SPHERICAL, VARIO_EXPONENTIAL, EST_SIMPLE, EST_ORDINARY, EST_UNIVERSAL,
                    FLAG_CLAMP_VARIANCE, FLAG_SQRT_ROUNDTRIP, FLAGS_DEFAULT, GSK_MAX_NEIGHBORS)

@@ -232,6 +232,8 @@ def load_library(path: os.PathLike | None = None):
     lib.gsk_synchronize.restype = C.c_int
     lib.gsk_krige.argtypes = [ctx, pp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.gsk_krige.restype = C.c_int
+    lib.gsk_krige_multi.argtypes = [_ip, C.c_int, pp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+    lib.gsk_krige_multi.restype = C.c_int
     lib.gsk_plan.argtypes = [ctx, pp]
     lib.gsk_plan.restype = C.c_int
     lib.gsk_execute.argtypes = [ctx, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -259,7 +261,7 @@ def load_library(path: os.PathLike | None = None):
 
 
 EXPORTED_SYMBOLS = [
-    "gsk_create", "gsk_destroy", "gsk_last_error", "gsk_set_stream", "gsk_synchronize", "gsk_krige", "gsk_plan",
+    "gsk_create", "gsk_destroy", "gsk_last_error", "gsk_set_stream", "gsk_synchronize", "gsk_krige", "gsk_krige_multi", "gsk_plan",
     "gsk_execute", "gsk_execute_peers", "gsk_get_timing", "gsk_set_phase_timing", "gsk_num_targets", "gsk_uk_exponents", "gsk_default_support",
     "gsk_measure_fp64_peak", "gsk_abi_version",
 ]
@@ -354,6 +356,28 @@ class Context:
         a, b = C.c_double(), C.c_double()
         self._check(self.lib.gsk_measure_fp64_peak(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+def krige_multi(spec: ProblemSpec, device_ids, want_neighbors: bool = False):
+    """Single-process multi-GPU call (``gsk_krige_multi``): the slab is split over ``device_ids``."""
+    lib = load_library()
+    first, count = spec.slab
+    mean = np.empty(count, dtype=np.float64)
+    var = np.empty(count, dtype=np.float64)
+    k = spec.params["max_neighbors"]
+    nneigh = np.empty(count, dtype=np.int32) if want_neighbors else None
+    idx = np.empty((count, max(k, 1)), dtype=np.int32) if (want_neighbors and k > 0) else None
+    ids = np.asarray(list(device_ids), dtype=np.int32)
+    err = C.create_string_buffer(512)
+    ps = spec.c_struct()
+    rc = lib.gsk_krige_multi(ids.ctypes.data_as(_ip), len(ids), C.byref(ps), mean.ctypes.data, var.ctypes.data,
+                             nneigh.ctypes.data if nneigh is not None else None,
+                             idx.ctypes.data if idx is not None else None, err, 512)
+    if rc != 0:
+        raise GskError(rc, err.value.decode())
+    if want_neighbors:
+        return mean, var, nneigh, idx
+    return mean, var
 
 
 # ------------------------------------------------------------------------------------

@@ -8,7 +8,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "gsk_internal.cuh"
 
@@ -620,4 +623,69 @@ extern "C" GSK_API int gsk_measure_fp64_peak(gsk_ctx *ctx, double *dfma_tflops, 
   if (!ctx || !dfma_tflops || !dmma_tflops) return GSK_ERR_INVALID;
   GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   return gsk_peak_measure(ctx, dfma_tflops, dmma_tflops);
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-process multi-GPU: one host thread + one cached context per piece
+// ---------------------------------------------------------------------------------------------
+namespace {
+std::mutex g_multi_mutex;
+std::vector<gsk_ctx *> g_multi_ctx;   // slot i serves piece i (re-created if the device id changes)
+}  // namespace
+
+extern "C" GSK_API int gsk_krige_multi(const int *device_ids, int n_devices, const gsk_problem *p, double *mean_out,
+                                       double *var_out, int32_t *nneigh_out, int32_t *neigh_idx_out, char *errbuf,
+                                       int errbuf_len) {
+  auto set_err = [&](const std::string &m) {
+    if (errbuf && errbuf_len > 0) {
+      strncpy(errbuf, m.c_str(), (size_t)errbuf_len - 1);
+      errbuf[errbuf_len - 1] = 0;
+    }
+  };
+  if (!device_ids || n_devices < 1 || n_devices > 64 || !p || !mean_out || !var_out) {
+    set_err("gsk_krige_multi: invalid arguments");
+    return GSK_ERR_INVALID;
+  }
+  std::lock_guard<std::mutex> lock(g_multi_mutex);  // one multi-GPU call at a time per process
+  if ((int)g_multi_ctx.size() < n_devices) g_multi_ctx.resize(n_devices, nullptr);
+  for (int i = 0; i < n_devices; ++i) {
+    if (g_multi_ctx[i] && g_multi_ctx[i]->device != device_ids[i]) {
+      gsk_destroy(g_multi_ctx[i]);
+      g_multi_ctx[i] = nullptr;
+    }
+    if (!g_multi_ctx[i]) {
+      int rc = gsk_create(&g_multi_ctx[i], device_ids[i]);
+      if (rc != GSK_OK) {
+        set_err(gsk_last_error(nullptr));
+        return rc;
+      }
+    }
+  }
+  const int64_t T = gsk_num_targets(p);
+  const int64_t first = p->target_first;
+  const int64_t count = p->target_count < 0 ? T - first : p->target_count;
+  if (first < 0 || count < 0 || first + count > T) {
+    set_err("gsk_krige_multi: target slab out of range");
+    return GSK_ERR_INVALID;
+  }
+  const int k = p->max_neighbors;
+  std::vector<int> rcs(n_devices, GSK_OK);
+  std::vector<std::thread> workers;
+  for (int i = 0; i < n_devices; ++i) {
+    workers.emplace_back([&, i]() {
+      const int64_t lo = count * i / n_devices, hi = count * (i + 1) / n_devices;
+      gsk_problem pi = *p;
+      pi.target_first = first + lo;
+      pi.target_count = hi - lo;
+      rcs[i] = gsk_krige(g_multi_ctx[i], &pi, mean_out + lo, var_out + lo, nneigh_out ? nneigh_out + lo : nullptr,
+                         (neigh_idx_out && k > 0) ? neigh_idx_out + lo * k : nullptr);
+    });
+  }
+  for (auto &w : workers) w.join();
+  for (int i = 0; i < n_devices; ++i)
+    if (rcs[i] != GSK_OK) {
+      set_err(gsk_last_error(g_multi_ctx[i]));
+      return rcs[i];
+    }
+  return GSK_OK;
 }

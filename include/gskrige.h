@@ -145,6 +145,16 @@ GSK_API int gsk_krige(gsk_ctx *ctx, const gsk_problem *prob,
               int32_t *nneigh_out,               /* optional: neighbours used per target (global: n_samples) */
               int32_t *neigh_idx_out);           /* optional: count × max_neighbors, 0-based, sorted by (d², idx), −1 padded */
 
+/* ---- single-process multi-GPU convenience (a Julia host drives all GPUs of a box from one process):
+ * the slab [target_first, target_first+target_count) is split into n_devices contiguous pieces, one host
+ * thread and one cached context per listed device computes its piece (samples replicated) and copies it
+ * straight into the caller's host arrays — no collective is needed when results return to host memory.
+ * device_ids may repeat (two pieces on one GPU). Returns the first failing piece's code; its message goes
+ * to errbuf (NUL-terminated, may be NULL). */
+GSK_API int gsk_krige_multi(const int *device_ids, int n_devices, const gsk_problem *prob, double *mean_out,
+                            double *var_out, int32_t *nneigh_out, int32_t *neigh_idx_out, char *errbuf,
+                            int errbuf_len);
+
 /* ---- resident two-step form: replaces preprocess' searcher/estimator construction
  *      (krig.jl:110,117; fit at krig.jl:176) and then the per-target loops ------------- */
 /* uploads samples, builds the bin structure (local) or assembles + factorises the

@@ -375,3 +375,21 @@ def test_execute_peers_stores_into_every_destination(gsk, ctx):
         with pytest.raises(gsk.GskError):
             own.execute_peers(first, count, [bufs[0][0].data_ptr()] * 9, [bufs[0][1].data_ptr()] * 9)
         own.close()
+
+
+def test_krige_multi_single_process(gsk, ctx):
+    """gsk_krige_multi: one process, several pieces (here three contexts on the one visible GPU) — the result
+    must equal the single-context call bit for bit, local and global paths."""
+    import torch
+    ids = [0, 0, 0] if torch.cuda.device_count() < 2 else [0, 1, 0]
+    for name, kw in (("C3b", dict(scale=0.12)), ("C1", dict(grid=(40, 30), n=250))):
+        spec = gsk.synth.config_spec(name, **kw)
+        ref = ctx.krige(spec, want_neighbors=True)
+        got = gsk.krige_multi(spec, ids, want_neighbors=True)
+        for a, b in zip(ref, got):
+            if a is not None:
+                assert np.array_equal(a, b, equal_nan=True)
+        part = gsk.krige_multi(spec.with_slab(100, 777), [0, 0])
+        assert np.array_equal(part[0], ref[0][100:877])
+    with pytest.raises(gsk.GskError):
+        gsk.krige_multi(spec, [99])
