@@ -15,12 +15,13 @@ namespace gsk_local {
 
 constexpr int SK_KMAX = 20;   // neighbour columns (multiple of 4)
 constexpr int SK_R = SK_KMAX / 4;
-constexpr int SK_STOR = col_off<SK_KMAX, 4>(SK_KMAX);  // packed factor, rows >= p & ~3 of column p
-constexpr int SK_GSZ = ((SK_STOR + 15) / 16) * 16 + 4;  // ≡ 4 (mod 16) doubles: groups spread over the banks
+constexpr int SK_STOR = col_off<SK_KMAX, 1>(SK_KMAX);  // tightly packed factor: column p keeps rows >= p
+constexpr int sk_pad(int g) { return ((g & 15) == 4 || (g & 15) == 12) ? g : sk_pad(g + 1); }
+constexpr int SK_GSZ = sk_pad(SK_STOR);  // ≡ 4 or 12 (mod 16) doubles: the groups of a warp spread over the banks
 
 template <int DIM, int VK>
-__global__ void __launch_bounds__(128, 3) local_solve_small_kernel(const GskLocalArgs a, const int KC) {
-  constexpr int G = 4, R = SK_R, W = 4, RT = SK_KMAX, A = 4, KM = SK_KMAX;
+__global__ void __launch_bounds__(128, 4) local_solve_small_kernel(const GskLocalArgs a, const int KC) {
+  constexpr int G = 4, R = SK_R, W = 4, RT = SK_KMAX, A = 1, KM = SK_KMAX;
   constexpr int TPC = 32;  // targets per CTA
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sm = reinterpret_cast<double *>(smem_raw);
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(128, 3) local_solve_small_kernel(const GskLoca
           double v = cov_fast<VK>(vg, d2);
           v = (i > p && i < nn) ? v : 0.0;
           v = (i == p) ? (valid_p ? vg.sill : 1.0) : v;
-          Sl[col_off<RT, A>(p) - sb + r * G] = v;
+          if (r * G >= p || i >= p) Sl[col_off<RT, A>(p) - p + r * G] = v;
         }
       }
     }
@@ -152,16 +153,15 @@ __global__ void __launch_bounds__(128, 3) local_solve_small_kernel(const GskLoca
       for (int r = 0; r < R; ++r)
         if (r >= rmin)
 #pragma unroll
-          for (int jj = 0; jj < W; ++jj) acc[r][jj] = Sl[col_off<RT, A>(c0 + jj) - c0 + r * G];
+          for (int jj = 0; jj < W; ++jj)
+            acc[r][jj] = (r * G >= c0 + jj || r * G + l >= c0 + jj) ? Sl[col_off<RT, A>(c0 + jj) - (c0 + jj) + r * G] : 0.0;
 #pragma unroll
       for (int jj = 0; jj < W; ++jj) accx[jj] = yreg[c0 + jj];
       // left-looking update from the finished columns
 #pragma unroll
       for (int p = 0; p < c0; ++p) {
-        const double *col = S + col_off<RT, A>(p) - (p & ~3);
-        const double2 t01 = *reinterpret_cast<const double2 *>(col + c0);
-        const double2 t23 = *reinterpret_cast<const double2 *>(col + c0 + 2);
-        const double piv[W] = {t01.x, t01.y, t23.x, t23.y};
+        const double *col = S + col_off<RT, A>(p) - p;
+        const double piv[W] = {col[c0], col[c0 + 1], col[c0 + 2], col[c0 + 3]};
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           if (r >= rmin) {
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(128, 3) local_solve_small_kernel(const GskLoca
         for (int r = 0; r < R; ++r) {
           if (r >= rmin) {
             acc[r][jj] *= rinv;
-            if (r * G >= j || r * G + l >= j) Sl[col_off<RT, A>(j) - c0 + r * G] = acc[r][jj];
+            if (r * G >= j || r * G + l >= j) Sl[col_off<RT, A>(j) - j + r * G] = acc[r][jj];
           }
         }
         accx[jj] *= rinv;
