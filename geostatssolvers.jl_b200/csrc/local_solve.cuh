@@ -110,11 +110,8 @@ __device__ __forceinline__ double gsk_exp_neg(double x) {
   p = fma(p, f, 0.5);
   p = fma(p, f, 1.0);
   p = fma(p, f, 1.0);
-  // scale by 2^n, n in [-1010, 0]: two steps keep the intermediate normal
-  const int n1 = n >> 1, n2 = n - n1;
-  const double s1 = __hiloint2double((1023 + n1) << 20, 0);
-  const double s2 = __hiloint2double((1023 + n2) << 20, 0);
-  return (p * s1) * s2;
+  // scale by 2^n through the exponent field: n >= round(-700·log2 e) = -1010, so 2^n is a normal number
+  return p * __hiloint2double((1023 + n) << 20, 0);
 }
 
 // covariance from the squared distance, fast-path math (same formulas as gsk_cov)
