@@ -332,6 +332,15 @@ extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) {
     if (rc != GSK_OK) return rc;
     GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_sup, sup.data(), sizeof(double) * sup.size(), cudaMemcpyHostToDevice,
                                         ctx->stream));
+    // block-support RHS shortcut for the exponential model (local_solve.cuh: rhs_block_support)
+    double dmax2 = 0.0;
+    for (int q = 0; q < p->n_support; ++q) {
+      double d2 = 0.0;
+      for (int d = 0; d < 3; ++d) d2 += sup[(size_t)d * p->n_support + q] * sup[(size_t)d * p->n_support + q];
+      dmax2 = std::max(dmax2, d2);
+    }
+    ctx->rhs_taylor = (p->vario_kind == GSK_VARIO_EXPONENTIAL && p->n_support > 1 &&
+                       3.0 * sqrt(dmax2) / p->vario_range <= 0.06 && !getenv("GSK_NO_RHS_TAYLOR")) ? 1 : 0;
     GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   }
 

@@ -73,6 +73,7 @@ struct GskLocalArgs {
   const double4 *rec_orig;  // samples in original order: {x, y, z, value}
   const double *sup;        // support offsets [3][nsup] (device)
   int nsup;
+  int rhs_taylor;           // exponential model with 3·max|δ|/range <= 0.06: one exp per neighbour + polynomial per support point
   int k;                    // clamped max neighbours
   int min_neighbors;
   int use_ball;
@@ -139,6 +140,7 @@ struct gsk_ctx {
   GskVario vg{};
   GskEstimator es{};
   int margin0[3] = {1, 1, 1};
+  int rhs_taylor = 0;
 
   // scratch that grows on demand
   int *d_nn = nullptr;

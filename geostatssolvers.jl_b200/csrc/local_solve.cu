@@ -12,6 +12,7 @@ int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long 
   a.rec_orig = ctx->d_rec_orig;
   a.sup = ctx->d_sup;
   a.nsup = ctx->prob.n_support;
+  a.rhs_taylor = ctx->rhs_taylor;
   a.k = ctx->prob.max_neighbors;
   a.min_neighbors = ctx->prob.min_neighbors;
   a.use_ball = !(ctx->prob.ball_radius != ctx->prob.ball_radius);

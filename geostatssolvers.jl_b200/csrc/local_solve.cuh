@@ -131,6 +131,77 @@ __device__ __forceinline__ double cov_fast(const GskVario &v, double d2) {
   return (d2 > 0.0) ? c : v.sill;
 }
 
+// Block-support right-hand side for the JM neighbours a lane owns:  bacc[jj] = Σ_q C(‖t + δ_q − x_jj‖).
+// q is the outer loop so that the JM evaluations are independent chains. For the exponential model with a
+// support that is small against the range (flag rhs_taylor, set on the host when 3·max|δ|/r <= 0.06) the
+// identity exp(−3h/r) = exp(−3h₀/r)·exp(−3(h−h₀)/r), |h − h₀| <= |δ|, needs ONE exp per neighbour and a degree-8
+// polynomial per support point (truncation <= 0.06⁹/9! = 3e-17 relative) instead of an exp per point.
+template <int VK, int DIM, int JM>
+__device__ __forceinline__ void rhs_block_support(const GskLocalArgs &a, const GskVario &vg, const double *sup,
+                                                  const double (&tc)[3], const double (&nx)[JM], const double (&ny)[JM],
+                                                  const double (&nz)[JM], double (&bacc)[JM]) {
+  if (VK == GSK_VARIO_EXPONENTIAL && a.rhs_taylor) {
+    double h0[JM], g[JM], zc[JM];
+    const double sc = -3.0 * vg.inv_r;
+#pragma unroll
+    for (int jj = 0; jj < JM; ++jj) {
+      const double dx = tc[0] - nx[jj], dy = tc[1] - ny[jj];
+      double d2 = fma(dy, dy, dx * dx);
+      if (DIM == 3) {
+        const double dz = tc[2] - nz[jj];
+        d2 = fma(dz, dz, d2);
+      }
+      h0[jj] = (d2 > 0.0) ? gsk_sqrt_pos(d2) : 0.0;
+      g[jj] = 0.0;
+      zc[jj] = 0.0;
+    }
+    for (int q = 0; q < a.nsup; ++q) {
+      const double ux = tc[0] + sup[q], uy = tc[1] + sup[a.nsup + q];
+      const double uz = (DIM == 3) ? tc[2] + sup[2 * a.nsup + q] : 0.0;
+#pragma unroll
+      for (int jj = 0; jj < JM; ++jj) {
+        const double dx = ux - nx[jj], dy = uy - ny[jj];
+        double d2 = fma(dy, dy, dx * dx);
+        if (DIM == 3) {
+          const double dz = uz - nz[jj];
+          d2 = fma(dz, dz, d2);
+        }
+        const bool pos = d2 > 0.0;
+        const double h = pos ? gsk_sqrt_pos(d2) : 0.0;
+        const double x = sc * (h - h0[jj]);
+        double p = 2.48015873015873015873e-05;      // 1/8!
+        p = fma(p, x, 1.98412698412698412698e-04);  // 1/7!
+        p = fma(p, x, 1.38888888888888888889e-03);
+        p = fma(p, x, 8.33333333333333333333e-03);
+        p = fma(p, x, 4.16666666666666666667e-02);
+        p = fma(p, x, 1.66666666666666666667e-01);
+        p = fma(p, x, 0.5);
+        p = fma(p, x, 1.0);
+        p = fma(p, x, 1.0);
+        g[jj] += pos ? p : 0.0;
+        zc[jj] += pos ? 0.0 : 1.0;   // a support point exactly on the sample contributes C(0) = sill
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < JM; ++jj) bacc[jj] = fma(vg.cs * gsk_exp_neg(sc * h0[jj]), g[jj], vg.sill * zc[jj]);
+    return;
+  }
+  for (int q = 0; q < a.nsup; ++q) {
+    const double ux = tc[0] + sup[q], uy = tc[1] + sup[a.nsup + q];
+    const double uz = (DIM == 3) ? tc[2] + sup[2 * a.nsup + q] : 0.0;
+#pragma unroll
+    for (int jj = 0; jj < JM; ++jj) {  // branch-free: the JM chains interleave (invalid lanes compute on zeros)
+      const double dx = ux - nx[jj], dy = uy - ny[jj];
+      double d2 = fma(dy, dy, dx * dx);
+      if (DIM == 3) {
+        const double dz = uz - nz[jj];
+        d2 = fma(dz, dz, d2);
+      }
+      bacc[jj] += cov_fast<VK>(vg, d2);
+    }
+  }
+}
+
 // G lanes per target, R register row slots (R·G >= RS), W panel width, RS rows stored per column,
 // NT threads per CTA
 template <int G, int R, int W, int RS, int NT, int DIM, int VK>
@@ -235,20 +306,7 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
         if (DIM == 3) nbZ[j] = rc.z;
       }
     }
-    for (int q = 0; q < a.nsup; ++q) {
-      const double ux = tc[0] + sup[q], uy = tc[1] + sup[a.nsup + q];
-      const double uz = (DIM == 3) ? tc[2] + sup[2 * a.nsup + q] : 0.0;
-#pragma unroll
-      for (int jj = 0; jj < JM; ++jj) {  // branch-free: the JM chains interleave (invalid lanes compute on zeros)
-        const double dx = ux - nx[jj], dy = uy - ny[jj];
-        double d2 = fma(dy, dy, dx * dx);
-        if (DIM == 3) {
-          const double dz = uz - nz[jj];
-          d2 = fma(dz, dz, d2);
-        }
-        bacc[jj] += cov_fast<VK>(vg, d2);
-      }
-    }
+    rhs_block_support<VK, DIM, JM>(a, vg, sup, tc, nx, ny, nz, bacc);
     const double inv_q = 1.0 / (double)a.nsup;
     const int nextra = RT - KC;
 #pragma unroll

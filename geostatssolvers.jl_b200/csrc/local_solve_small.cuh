@@ -86,20 +86,7 @@ __global__ void __launch_bounds__(128, 4) local_solve_small_kernel(const GskLoca
     bacc[jj] = 0.0;
   }
   // ---- phase 2: block-support RHS, q outermost (5 independent chains per lane) ----
-  for (int q = 0; q < a.nsup; ++q) {
-    const double ux = tc[0] + sup[q], uy = tc[1] + sup[a.nsup + q];
-    const double uz = (DIM == 3) ? tc[2] + sup[2 * a.nsup + q] : 0.0;
-#pragma unroll
-    for (int jj = 0; jj < R; ++jj) {
-      const double dx = ux - nx[jj], dy = uy - ny[jj];
-      double d2 = fma(dy, dy, dx * dx);
-      if (DIM == 3) {
-        const double dz = uz - nz[jj];
-        d2 = fma(dz, dz, d2);
-      }
-      bacc[jj] += cov_fast<VK>(vg, d2);
-    }
-  }
+  rhs_block_support<VK, DIM, R>(a, vg, sup, tc, nx, ny, nz, bacc);
   // ---- phase 3: extra rows into registers: lane 0 ← b, lane 1 ← z, lane 2 ← ones (OK), lane 3 ← 0 ----
   double yreg[KM];
   {
