@@ -237,6 +237,24 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
   const int gbase = lane - l;  // first lane of my group in the warp
   const int KC = L.KC, e = L.e, EPr = L.EPr;
 
+  const long long t = (long long)blockIdx.x * TPC + grp;  // slab-local target
+  const bool live = t < a.count;
+  // issue the neighbour-index loads and the dependent record loads first: their latency overlaps the
+  // support staging, the barrier and the centroid arithmetic
+  constexpr int JM = (KCMAX + G - 1) / G;
+  int nidx[JM];
+#pragma unroll
+  for (int jj = 0; jj < JM; ++jj) {
+    const int j = jj * G + l;
+    nidx[jj] = (live && j < a.k) ? a.nbr[t * a.k + j] : -1;  // −1 padded beyond nn: no dependence on the nn load
+  }
+  double4 nrec[JM];
+#pragma unroll
+  for (int jj = 0; jj < JM; ++jj) {
+    nrec[jj] = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (nidx[jj] >= 0) nrec[jj] = a.rec_orig[nidx[jj]];
+  }
+
   for (int i = tid; i < 3 * a.nsup; i += CTA_THREADS) sup[i] = a.sup[i];
   __syncthreads();
 
@@ -245,9 +263,6 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
   double *nbY = nbX + KCMAX;
   double *nbZ = (DIM == 3) ? nbY + KCMAX : nbY;
   double *GM = S + L.off_gm;
-
-  const long long t = (long long)blockIdx.x * TPC + grp;  // slab-local target
-  const bool live = t < a.count;
   const GskVario vg = a.vg;
 
   // ---- target centroid ----
@@ -289,15 +304,12 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
   // ---- phase 1+2: gather my neighbours (j = l, l+G, …) into registers; block-support RHS
   //      b_j = mean_q C(‖t + δ_q − x_j‖) with the q loop outermost so that the JM evaluations of a
   //      lane are independent (ILP); write the extra rows of column j ----
-  constexpr int JM = (KCMAX + G - 1) / G;
   {
     double nx[JM], ny[JM], nz[JM], nv[JM], bacc[JM];
 #pragma unroll
     for (int jj = 0; jj < JM; ++jj) {
       const int j = jj * G + l;
-      double4 rc = make_double4(0.0, 0.0, 0.0, 0.0);
-      const int idx = (live && j < a.k) ? a.nbr[t * a.k + j] : -1;  // −1 padded beyond nn: no dependence on the nn load
-      if (idx >= 0) rc = a.rec_orig[idx];
+      const double4 rc = nrec[jj];
       nx[jj] = rc.x; ny[jj] = rc.y; nz[jj] = rc.z; nv[jj] = rc.w;
       bacc[jj] = 0.0;
       if (j < KC) {

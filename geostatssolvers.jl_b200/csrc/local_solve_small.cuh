@@ -28,13 +28,26 @@ __global__ void __launch_bounds__(128, 4) local_solve_small_kernel(const GskLoca
   double *sup = sm;
   const int nsup_pad = (3 * a.nsup + 3) & ~3;
   const int tid = threadIdx.x, lane = tid & 31, l = lane & 3, grp = tid >> 2, gbase = lane & ~3;
+  const long long t = (long long)blockIdx.x * TPC + grp;
+  const bool live = t < a.count;
+  // issue the neighbour-index loads first: their latency (and that of the dependent record loads below) then
+  // overlaps the support staging, the barrier and the centroid arithmetic
+  int nidx[SK_R];
+#pragma unroll
+  for (int jj = 0; jj < SK_R; ++jj) {
+    const int j = jj * 4 + l;
+    nidx[jj] = (live && j < a.k) ? a.nbr[t * a.k + j] : -1;
+  }
+  double4 nrec[SK_R];
+#pragma unroll
+  for (int jj = 0; jj < SK_R; ++jj) {
+    nrec[jj] = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (nidx[jj] >= 0) nrec[jj] = a.rec_orig[nidx[jj]];
+  }
   for (int i = tid; i < 3 * a.nsup; i += 128) sup[i] = a.sup[i];
   __syncthreads();
   double *S = sm + nsup_pad + (size_t)grp * SK_GSZ;
   double *Sl = S + l;
-
-  const long long t = (long long)blockIdx.x * TPC + grp;
-  const bool live = t < a.count;
   const GskVario vg = a.vg;
 
   // ---- target centroid ----
@@ -77,10 +90,7 @@ __global__ void __launch_bounds__(128, 4) local_solve_small_kernel(const GskLoca
   double nx[R], ny[R], nz[R], nv[R], bacc[R];
 #pragma unroll
   for (int jj = 0; jj < R; ++jj) {
-    const int j = jj * G + l;
-    double4 rc = make_double4(0.0, 0.0, 0.0, 0.0);
-    const int idx = (live && j < a.k) ? a.nbr[t * a.k + j] : -1;
-    if (idx >= 0) rc = a.rec_orig[idx];
+    const double4 rc = nrec[jj];
     nx[jj] = rc.x; ny[jj] = rc.y; nz[jj] = rc.z;
     nv[jj] = (a.es.kind == GSK_EST_SIMPLE) ? rc.w - a.es.sk_mean : rc.w;
     bacc[jj] = 0.0;
