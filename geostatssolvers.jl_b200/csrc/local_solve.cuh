@@ -186,6 +186,7 @@ __device__ __forceinline__ void rhs_block_support(const GskLocalArgs &a, const G
     for (int jj = 0; jj < JM; ++jj) bacc[jj] = fma(vg.cs * gsk_exp_neg(sc * h0[jj]), g[jj], vg.sill * zc[jj]);
     return;
   }
+#pragma unroll 3
   for (int q = 0; q < a.nsup; ++q) {
     const double ux = tc[0] + sup[q], uy = tc[1] + sup[a.nsup + q];
     const double uz = (DIM == 3) ? tc[2] + sup[2 * a.nsup + q] : 0.0;

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(128, 4) local_solve_small_kernel(const GskLoca
     const int j = jj * 4 + l;
     nidx[jj] = (live && j < a.k) ? a.nbr[t * a.k + j] : -1;
   }
+  const int nn_in = live ? a.nn[t] : 0;
   double4 nrec[SK_R];
 #pragma unroll
   for (int jj = 0; jj < SK_R; ++jj) {
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(128, 4) local_solve_small_kernel(const GskLoca
     } else {
       for (int d = 0; d < a.tg.dim; ++d) tc[d] = a.tg.pts[d][lin];
     }
-    nn = a.nn[t];
+    nn = nn_in;
   }
   const bool estimate = live && nn >= a.min_neighbors && nn > 0;
   if (!estimate) nn = 0;
