@@ -283,6 +283,8 @@ extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) {
   v.inv_r2 = v.inv_r * v.inv_r;
   v.hcs = 0.5 * v.cs;
   v.m15cs = -1.5 * v.cs;
+  v.m3ir2 = -3.0 * v.inv_r2;
+  v.m3ir = -3.0 * v.inv_r;
 
   // estimator
   GskEstimator &es = ctx->es;

@@ -27,6 +27,7 @@ struct GskVario {
   double inv_r2;  // 1/r²
   double inv_r;   // 1/r
   double hcs, m15cs;  // 0.5·cs, −1.5·cs (spherical polynomial with cs folded in)
+  double m3ir2, m3ir; // −3/r², −3/r (exponent scales of the Gaussian and exponential models)
 };
 
 struct GskTargets {

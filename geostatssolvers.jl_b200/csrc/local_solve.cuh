@@ -114,21 +114,28 @@ __device__ __forceinline__ double gsk_exp_neg(double x) {
   return p * __hiloint2double((1023 + n) << 20, 0);
 }
 
+// Sign/magnitude tests on the high word run on the integer pipe instead of the FP64 pipe (DSETP), which is the
+// pipe the kernels saturate. Valid for finite d >= 0; a subnormal d (distance below 1.5e-154) counts as zero —
+// rsqrt.approx.ftz flushes it to zero anyway.
+__device__ __forceinline__ bool gsk_is_pos(double d) { return __double2hiint(d) != 0; }
+__device__ __forceinline__ bool gsk_lt_one(double d) { return __double2hiint(d) < 0x3FF00000; }
+
 // covariance from the squared distance, fast-path math (same formulas as gsk_cov)
-template <int VK>
+// UNIT: the coordinates were divided by the range beforehand, d2 is (h/r)² (spherical model only)
+template <int VK, bool UNIT = false>
 __device__ __forceinline__ double cov_fast(const GskVario &v, double d2) {
   double c;
   if (VK == GSK_VARIO_GAUSSIAN) {
-    c = v.cs * gsk_exp_neg(-3.0 * d2 * v.inv_r2);
+    c = v.cs * gsk_exp_neg(d2 * v.m3ir2);
   } else if (VK == GSK_VARIO_SPHERICAL) {
-    const double u = d2 * v.inv_r2;
+    const double u = UNIT ? d2 : d2 * v.inv_r2;
     const double t = gsk_sqrt_pos(u);
-    c = (u < 1.0) ? fma(t, fma(v.hcs, u, v.m15cs), v.cs) : 0.0;  // cs(1 − 1.5t + 0.5t³)
+    c = gsk_lt_one(u) ? fma(t, fma(v.hcs, u, v.m15cs), v.cs) : 0.0;  // cs(1 − 1.5t + 0.5t³)
   } else {
-    const double h = (d2 > 0.0) ? gsk_sqrt_pos(d2) : 0.0;
-    c = v.cs * gsk_exp_neg(-3.0 * v.inv_r * h);
+    const double h = gsk_is_pos(d2) ? gsk_sqrt_pos(d2) : 0.0;
+    c = v.cs * gsk_exp_neg(v.m3ir * h);
   }
-  return (d2 > 0.0) ? c : v.sill;
+  return gsk_is_pos(d2) ? c : v.sill;
 }
 
 // Block-support right-hand side for the JM neighbours a lane owns:  bacc[jj] = Σ_q C(‖t + δ_q − x_jj‖).
@@ -136,13 +143,13 @@ __device__ __forceinline__ double cov_fast(const GskVario &v, double d2) {
 // support that is small against the range (flag rhs_taylor, set on the host when 3·max|δ|/r <= 0.06) the
 // identity exp(−3h/r) = exp(−3h₀/r)·exp(−3(h−h₀)/r), |h − h₀| <= |δ|, needs ONE exp per neighbour and a degree-8
 // polynomial per support point (truncation <= 0.06⁹/9! = 3e-17 relative) instead of an exp per point.
-template <int VK, int DIM, int JM>
+template <int VK, int DIM, int JM, bool UNIT = false>
 __device__ __forceinline__ void rhs_block_support(const GskLocalArgs &a, const GskVario &vg, const double *sup,
                                                   const double (&tc)[3], const double (&nx)[JM], const double (&ny)[JM],
                                                   const double (&nz)[JM], double (&bacc)[JM]) {
   if (VK == GSK_VARIO_EXPONENTIAL && a.rhs_taylor) {
     double h0[JM], g[JM], zc[JM];
-    const double sc = -3.0 * vg.inv_r;
+    const double sc = vg.m3ir;
 #pragma unroll
     for (int jj = 0; jj < JM; ++jj) {
       const double dx = tc[0] - nx[jj], dy = tc[1] - ny[jj];
@@ -151,7 +158,7 @@ __device__ __forceinline__ void rhs_block_support(const GskLocalArgs &a, const G
         const double dz = tc[2] - nz[jj];
         d2 = fma(dz, dz, d2);
       }
-      h0[jj] = (d2 > 0.0) ? gsk_sqrt_pos(d2) : 0.0;
+      h0[jj] = gsk_is_pos(d2) ? gsk_sqrt_pos(d2) : 0.0;
       g[jj] = 0.0;
       zc[jj] = 0.0;
     }
@@ -166,7 +173,7 @@ __device__ __forceinline__ void rhs_block_support(const GskLocalArgs &a, const G
           const double dz = uz - nz[jj];
           d2 = fma(dz, dz, d2);
         }
-        const bool pos = d2 > 0.0;
+        const bool pos = gsk_is_pos(d2);
         const double h = pos ? gsk_sqrt_pos(d2) : 0.0;
         const double x = sc * (h - h0[jj]);
         double p = 2.48015873015873015873e-05;      // 1/8!
@@ -198,7 +205,7 @@ __device__ __forceinline__ void rhs_block_support(const GskLocalArgs &a, const G
         const double dz = uz - nz[jj];
         d2 = fma(dz, dz, d2);
       }
-      bacc[jj] += cov_fast<VK>(vg, d2);
+      bacc[jj] += cov_fast<VK, UNIT>(vg, d2);
     }
   }
 }

@@ -45,7 +45,11 @@ __global__ void __launch_bounds__(128, 4) local_solve_small_kernel(const GskLoca
     nrec[jj] = make_double4(0.0, 0.0, 0.0, 0.0);
     if (nidx[jj] >= 0) nrec[jj] = a.rec_orig[nidx[jj]];
   }
-  for (int i = tid; i < 3 * a.nsup; i += 128) sup[i] = a.sup[i];
+  // spherical model: lengths in units of the range, so that d² is the polynomial's argument (one DMUL less per
+  // evaluation; no drift terms here that would need the coordinates themselves)
+  constexpr bool UNIT = (VK == GSK_VARIO_SPHERICAL);
+  const double cscale = UNIT ? a.vg.inv_r : 1.0;
+  for (int i = tid; i < 3 * a.nsup; i += 128) sup[i] = UNIT ? a.sup[i] * cscale : a.sup[i];
   __syncthreads();
   double *S = sm + nsup_pad + (size_t)grp * SK_GSZ;
   double *Sl = S + l;
@@ -92,12 +96,17 @@ __global__ void __launch_bounds__(128, 4) local_solve_small_kernel(const GskLoca
 #pragma unroll
   for (int jj = 0; jj < R; ++jj) {
     const double4 rc = nrec[jj];
-    nx[jj] = rc.x; ny[jj] = rc.y; nz[jj] = rc.z;
+    // (relative to the target centroid before scaling: scaling absolute coordinates would lose digits in the
+    // differences taken below)
+    nx[jj] = UNIT ? (rc.x - tc[0]) * cscale : rc.x;
+    ny[jj] = UNIT ? (rc.y - tc[1]) * cscale : rc.y;
+    nz[jj] = UNIT ? (rc.z - tc[2]) * cscale : rc.z;
     nv[jj] = (a.es.kind == GSK_EST_SIMPLE) ? rc.w - a.es.sk_mean : rc.w;
     bacc[jj] = 0.0;
   }
   // ---- phase 2: block-support RHS, q outermost (5 independent chains per lane) ----
-  rhs_block_support<VK, DIM, R>(a, vg, sup, tc, nx, ny, nz, bacc);
+  if (UNIT) tc[0] = tc[1] = tc[2] = 0.0;  // the centroid is the local origin
+  rhs_block_support<VK, DIM, R, UNIT>(a, vg, sup, tc, nx, ny, nz, bacc);
   // ---- phase 3: extra rows into registers: lane 0 ← b, lane 1 ← z, lane 2 ← ones (OK), lane 3 ← 0 ----
   double yreg[KM];
   {
@@ -131,7 +140,7 @@ __global__ void __launch_bounds__(128, 4) local_solve_small_kernel(const GskLoca
             const double dz = nz[r] - zp;
             d2 = fma(dz, dz, d2);
           }
-          double v = cov_fast<VK>(vg, d2);
+          double v = cov_fast<VK, UNIT>(vg, d2);
           v = (i > p && i < nn) ? v : 0.0;
           v = (i == p) ? (valid_p ? vg.sill : 1.0) : v;
           if (r * G >= p || i >= p) Sl[col_off<RT, A>(p) - p + r * G] = v;

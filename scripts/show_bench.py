@@ -1,5 +1,7 @@
 import sys, json
-for l in sys.stdin:
+# usage: show_bench.py FILE   or   ... | show_bench.py -   (never waits on a terminal/inherited stdin by accident)
+src = open(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1] != "-" else sys.stdin
+for l in src:
     try:
         d = json.loads(l)
     except Exception:
