@@ -189,7 +189,7 @@ GSK_API int gsk_uk_exponents(int degree, int dim, int32_t *out, int out_capacity
 GSK_API int gsk_default_support(int dim, const double *spacing, double vario_range,
                         double *off_x, double *off_y, double *off_z, int capacity);
 /* measured FP64 peaks of the context's device (roofline denominators): a dependent-free
- * DFMA loop and an mma.sync m8n8k4 f64 (DMMA) loop, TFLOP/s */
+ * DFMA loop and an mma.sync m16n8k16 f64 (DMMA) loop, TFLOP/s */
 GSK_API int gsk_measure_fp64_peak(gsk_ctx *ctx, double *dfma_tflops, double *dmma_tflops);
 GSK_API int gsk_abi_version(void);
 

@@ -393,3 +393,33 @@ def test_krige_multi_single_process(gsk, ctx):
         assert np.array_equal(part[0], ref[0][100:877])
     with pytest.raises(gsk.GskError):
         gsk.krige_multi(spec, [99])
+
+
+def test_plain_c_host_end_to_end(gsk, oracle, tmp_path):
+    """The C-ABI without Python in the process: examples/krige_c.c (C99) runs C2 at 1/20 scale from files."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    lib_dir = root / "geostatssolvers.jl_b200" / "csrc"
+    exe = tmp_path / "krige_c"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", f"-I{root / 'include'}",
+                    str(root / "examples" / "krige_c.c"), f"-L{lib_dir}", "-lgskrige", f"-Wl,-rpath,{lib_dir}", "-lm",
+                    "-o", str(exe)], check=True)
+    spec = gsk.synth.config_spec("C2", scale=0.05)
+    gx, gy = spec.grid_dims
+    with open(tmp_path / "in.bin", "wb") as f:
+        np.array([spec.n_samples, gx, gy, spec.params["max_neighbors"]], dtype="<i8").tofile(f)
+        np.array([spec.params["vario_range"]], dtype="<f8").tofile(f)
+        for a in (spec.coords[0], spec.coords[1], spec.values):
+            np.ascontiguousarray(a, dtype="<f8").tofile(f)
+    r = subprocess.run([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True,
+                       timeout=120)
+    assert r.returncode == 0, r.stderr
+    T = gx * gy
+    raw = (tmp_path / "out.bin").read_bytes()
+    mean = np.frombuffer(raw, dtype="<f8", count=T)
+    var = np.frombuffer(raw, dtype="<f8", count=T, offset=8 * T)
+    nn = np.frombuffer(raw, dtype="<i4", count=T, offset=16 * T)
+    om, ov, onn, _ = oracle.krige(spec, want_neighbors=True)
+    assert np.array_equal(nn, onn)
+    assert_parity(mean, var, om, ov, scale=max(1.0, np.abs(spec.values).max()))

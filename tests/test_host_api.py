@@ -149,3 +149,18 @@ def test_host_mirror_errors(gsk):
         f = _FakeCtx()
         gsk.solve(prob, gsk.KrigingSolver(z=dict(maxneighbors=5)), ctx=f)
     assert f.specs[0].params["max_neighbors"] == 2
+
+
+def test_plain_c_host_compiles_against_the_header(gsk, tmp_path):
+    """examples/krige_c.c is a C99 host (what a ccall-style binding does); it must build with the header alone."""
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    lib_dir = root / "geostatssolvers.jl_b200" / "csrc"
+    exe = tmp_path / "krige_c"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{root / 'include'}",
+                        str(root / "examples" / "krige_c.c"), f"-L{lib_dir}", "-lgskrige", f"-Wl,-rpath,{lib_dir}", "-lm",
+                        "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)      # usage error, no compute call
+    assert r.returncode == 2 and "usage" in r.stderr
