@@ -39,6 +39,13 @@ __host__ __device__ constexpr int col_off(int p) {
   return p * RT - A * A * ((p / A) * ((p / A) - 1) / 2) - A * (p / A) * (p % A);
 }
 
+// Leading dimension of the column-packed factor: column p holds rows [s_p, LD) of which [s_p, RS) are used.
+// One warp per target (G = 32) updates its panels with the FP64 tensor instruction, whose operand fragments
+// read 4 columns × 8 rows per half-warp: a stride ≡ 4 (mod 8) doubles spreads those over all banks. The
+// 96-neighbour configuration (RS = 112) has no shared memory left for the padding.
+template <int G, int RS>
+__host__ __device__ constexpr int lead_dim() { return (G == 32 && RS <= 80) ? RS + 4 : RS; }
+
 struct Layout {
   int KC;    // neighbour columns, padded to a multiple of W
   int e;     // live extra rows (2 + c)
@@ -49,12 +56,12 @@ struct Layout {
 
 template <int G, int R, int W, int RS, int DIM>
 __host__ inline Layout make_layout(int k, int e) {
-  constexpr int RT = RS, A = col_align<W>(), KCMAX = RT - W;
+  constexpr int RT = RS, A = col_align<W>(), KCMAX = RT - W, LD = lead_dim<G, RS>();
   Layout L;
   L.KC = (k + W - 1) / W * W;
   L.e = e;
   L.EPr = (e + W - 1) / W * W;
-  int o = col_off<RT, A>(KCMAX);  // factor storage (static maximum); multiple of 4 doubles
+  int o = col_off<LD, A>(KCMAX);  // factor storage (static maximum); multiple of 4 doubles
   L.off_nb = o;
   o += DIM * KCMAX;
   L.off_gm = o;
@@ -112,6 +119,18 @@ __device__ __forceinline__ double gsk_exp_neg(double x) {
   p = fma(p, f, 1.0);
   // scale by 2^n through the exponent field: n >= round(-700·log2 e) = -1010, so 2^n is a normal number
   return p * __hiloint2double((1023 + n) << 20, 0);
+}
+
+// D(16×8) = A(16×16, row) · B(16×8, col) + D on the FP64 tensor path (SASS DMMA). Fragment layout, g = lane/4,
+// t = lane%4 (checked by scripts/dev/dmma_layout_test.cu): a[i] = A[g + 8(i&1)][t + 4(i>>1)], b[i] = B[t + 4i][g],
+// d = {D[g][2t], D[g][2t+1], D[g+8][2t], D[g+8][2t+1]}.
+__device__ __forceinline__ void gsk_dmma16816(double (&d)[4], const double (&a)[8], const double (&b)[4]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+      "{%12,%13,%14,%15}, {%0,%1,%2,%3};"
+      : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]), "d"(b[1]),
+        "d"(b[2]), "d"(b[3]));
 }
 
 // Sign/magnitude tests on the high word run on the integer pipe instead of the FP64 pipe (DSETP), which is the
@@ -218,7 +237,9 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
   constexpr int CTA_THREADS = NT;
   constexpr int RT = RS;
   constexpr int A = col_align<W>();
+  constexpr int LD = lead_dim<G, RS>();  // column stride base (>= RT)
   constexpr int KCMAX = RT - W;
+  constexpr bool USE_MMA = (G == 32 && W == 8 && A == 8);  // panel updates on the FP64 tensor path (DMMA)
   constexpr int TPW = 32 / G;
   constexpr int TPC = TPW * (CTA_THREADS / 32);
   constexpr bool UNROLL_P = (G == 4);  // small systems: unroll the left-looking loops completely
@@ -334,7 +355,7 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
       const int j = jj * G + l;
       if (j < KC) {
         const bool valid = j < nn;
-        double *colj = S + col_off<RT, A>(j) - (j & ~(A - 1));
+        double *colj = S + col_off<LD, A>(j) - (j & ~(A - 1));
         colj[KC] = valid ? bacc[jj] * inv_q : 0.0;
         colj[KC + 1] = valid ? ((a.es.kind == GSK_EST_SIMPLE) ? nv[jj] - a.es.sk_mean : nv[jj]) : 0.0;
         for (int r2 = 2; r2 < nextra; ++r2) {
@@ -375,7 +396,7 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
           const int p = sb + pp;
           const bool valid_p = p < nn;
           const double xp = nbX[p], yp = nbY[p], zp = (DIM == 3) ? nbZ[p] : 0.0;
-          double *col = S + col_off<RT, A>(sb) + pp * (RT - sb) - sb + l;
+          double *col = S + col_off<LD, A>(sb) + pp * (LD - sb) - sb + l;
 #pragma unroll
           for (int r = 0; r < RS_S; ++r) {
             if (SLOT_LIVE(r, sb) && ROW0(r) < KCMAX) {  // static after unrolling; slots of pure extra rows are skipped
@@ -404,6 +425,61 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
 #pragma unroll
   for (int c0 = 0; c0 < KCMAX; c0 += W) {
     if (c0 < KC) {
+      if (USE_MMA && c0 > 0) {
+        // Left-looking update of the panel, in place in shared memory, as one GEMM on the tensor path:
+        //   P[c0:RT, c0:c0+8] −= L[c0:RT, 0:c0] · L[c0:c0+8, 0:c0]ᵀ
+        // 16-row tiles × 16-column chunks of mma.m16n8k16; the tiles are independent chains. Rows past RT and
+        // columns past c0 in the last tile/chunk are zero operands (decided statically).
+        constexpr int MT_MAX = (RT - W + 15) / 16;
+        const int g8 = lane >> 2, t4 = lane & 3;
+        const int cpan = col_off<LD, A>(c0) - c0 + 2 * t4 * (LD - c0) + g8;  // element (row g8, column c0 + 2·t4)
+        double cf[MT_MAX][4];
+#pragma unroll
+        for (int m = 0; m < MT_MAX; ++m) {
+          if (c0 + 16 * m < RT) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const bool rows_ok = c0 + 16 * m + 8 * (c >> 1) < RT;
+              cf[m][c] = rows_ok ? S[cpan + (c & 1) * (LD - c0) + c0 + 16 * m + 8 * (c >> 1)] : 0.0;
+            }
+          }
+        }
+#pragma unroll
+        for (int p0 = 0; p0 < KCMAX; p0 += 16) {
+          if (p0 < c0) {
+            int cb[4];  // S index of (row g8, column p0 + 4i + t4)
+            double bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int pc = p0 + 4 * i, sg = pc & ~(A - 1);
+              cb[i] = col_off<LD, A>(sg) - sg + (pc - sg + t4) * (LD - sg) + g8;
+              bf[i] = (pc < c0) ? -S[cb[i] + c0] : 0.0;
+            }
+#pragma unroll
+            for (int m = 0; m < MT_MAX; ++m) {
+              if (c0 + 16 * m < RT) {
+                double af[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const bool ok = (p0 + 4 * (i >> 1) < c0) && (c0 + 16 * m + 8 * (i & 1) < RT);
+                  af[i] = ok ? S[cb[i >> 1] + c0 + 16 * m + 8 * (i & 1)] : 0.0;
+                }
+                gsk_dmma16816(cf[m], af, bf);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < MT_MAX; ++m) {
+          if (c0 + 16 * m < RT) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c0 + 16 * m + 8 * (c >> 1) < RT) S[cpan + (c & 1) * (LD - c0) + c0 + 16 * m + 8 * (c >> 1)] = cf[m][c];
+            }
+          }
+        }
+        __syncwarp();
+      }
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         if (SLOT_LIVE(r, c0)) {
@@ -412,13 +488,13 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
             const int j = c0 + jj;
             const int sj = j & ~(A - 1);
             const bool in = (ROW0(r) >= sj) || (ROW0(r) + l >= sj);
-            acc[r][jj] = in ? Sl[col_off<RT, A>(j) - sj + ROW0(r)] : 0.0;
+            acc[r][jj] = in ? Sl[col_off<LD, A>(j) - sj + ROW0(r)] : 0.0;
           }
         }
       }
       // left-looking update from the finished columns p < c0
       auto update = [&](int p) {
-        const double *col = S + col_off<RT, A>(p) - (p & ~(A - 1));
+        const double *col = S + col_off<LD, A>(p) - (p & ~(A - 1));
         double piv[W];
 #pragma unroll
         for (int jj = 0; jj < W; jj += 2) {
@@ -435,7 +511,9 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
           }
         }
       };
-      if (UNROLL_P) {
+      if (USE_MMA) {
+        // done above
+      } else if (UNROLL_P) {
 #pragma unroll
         for (int p = 0; p < c0; ++p) update(p);
       } else {
@@ -446,7 +524,7 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
         const double *colp = S;
 #pragma unroll 1
         for (int pg = 0; pg < c0; pg += A) {
-          const int stride = RT - pg;
+          const int stride = LD - pg;
 #pragma unroll
           for (int pp = 0; pp < A; ++pp) {
             double piv[W];
@@ -480,7 +558,7 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
         for (int r = 0; r < R; ++r) {
           if (SLOT_LIVE(r, c0)) {
             acc[r][jj] *= rinv;
-            if (ROW0(r) >= j || ROW0(r) + l >= j) Sl[col_off<RT, A>(j) - sj + ROW0(r)] = acc[r][jj];
+            if (ROW0(r) >= j || ROW0(r) + l >= j) Sl[col_off<LD, A>(j) - sj + ROW0(r)] = acc[r][jj];
           }
         }
 #pragma unroll
@@ -509,7 +587,7 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
         const double *col = S;  // col[i] = element (row i, column p); same group-wise stride as in phase 4
 #pragma unroll 1
         for (int pg = 0; pg < KC; pg += A) {
-          const int stride = RT - pg;
+          const int stride = LD - pg;
 #pragma unroll
           for (int pp = 0; pp < A; ++pp) {
             const double own = mine ? col[i] : 0.0;
