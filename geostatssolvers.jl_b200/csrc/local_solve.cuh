@@ -575,7 +575,35 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
   }
 
   // ---- phase 5: Schur complement of the extra rows: Gm = Y Yᵀ (only the slots that hold extra rows work) ----
-  for (int cc = 0; cc < EPr; cc += W) {
+  if (USE_MMA) {
+    // one 16-row tile holds all extra rows (EPr <= 16); Y Yᵀ needs the same fragment as A and as B
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const bool two = EPr > 8;  // rows / columns 8..15 exist
+    double d0[4] = {0.0, 0.0, 0.0, 0.0}, d1[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int p0 = 0; p0 < KC; p0 += 16) {
+      double lo[4], hi[4];  // Y[g8][p0 + 4i + t4], Y[g8 + 8][·]
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int pc = p0 + 4 * i, sg = pc & ~(A - 1);
+        const bool kin = pc < KC;  // KC is a multiple of 8: the last chunk may be half empty
+        const int cb = col_off<LD, A>(sg) - sg + (pc - sg + t4) * (LD - sg) + g8 + KC;
+        lo[i] = kin ? S[cb] : 0.0;
+        hi[i] = (kin && two) ? S[cb + 8] : 0.0;
+      }
+      const double af[8] = {lo[0], hi[0], lo[1], hi[1], lo[2], hi[2], lo[3], hi[3]};
+      gsk_dmma16816(d0, af, lo);
+      if (two) gsk_dmma16816(d1, af, hi);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int row = g8 + 8 * (c >> 1), col = 2 * t4 + (c & 1);
+      if (row < EPr) {
+        GM[row * EPr + col] = d0[c];
+        if (two) GM[row * EPr + 8 + col] = d1[c];
+      }
+    }
+  }
+  for (int cc = 0; cc < (USE_MMA ? 0 : EPr); cc += W) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       if (ROW0(r) + G > KC && ROW0(r) < KC + EPr) {  // slot holds extra rows (warp-uniform)
