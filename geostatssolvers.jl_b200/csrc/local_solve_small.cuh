@@ -5,8 +5,8 @@
 //     every shared-memory address is base + immediate and every register index is static;
 //   * the extra rows (b, z, ones) never touch shared memory: lane l keeps extra row l in registers
 //     (yreg[20]); they are updated alongside the neighbour rows and their Gram products are formed with
-//     shuffles — shared memory per target is just the packed factor (244 doubles = 1952 B), so three
-//     128-thread CTAs (96 targets) fit per SM instead of two;
+//     shuffles — shared memory per target is just the tightly packed factor (212 doubles = 1696 B), so 512
+//     threads (128 targets, two 256-thread CTAs) are resident per SM, the limit the 128 registers set too;
 //   * pivot column coordinates, pivots and panel rows all travel by warp shuffles inside the 4-lane group.
 #pragma once
 #include "local_solve.cuh"
@@ -19,10 +19,11 @@ constexpr int SK_STOR = col_off<SK_KMAX, 1>(SK_KMAX);  // tightly packed factor:
 constexpr int sk_pad(int g) { return ((g & 15) == 4 || (g & 15) == 12) ? g : sk_pad(g + 1); }
 constexpr int SK_GSZ = sk_pad(SK_STOR);  // ≡ 4 or 12 (mod 16) doubles: the groups of a warp spread over the banks
 
-template <int DIM, int VK>
-__global__ void __launch_bounds__(128, 4) local_solve_small_kernel(const GskLocalArgs a, const int KC) {
+// NTH threads per CTA (NTH/4 targets); 512 threads per SM either way — 256 measured 1 % ahead of 64/128, 512 8 % behind
+template <int DIM, int VK, int NTH = 256>
+__global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const GskLocalArgs a, const int KC) {
   constexpr int G = 4, R = SK_R, W = 4, RT = SK_KMAX, A = 1, KM = SK_KMAX;
-  constexpr int TPC = 32;  // targets per CTA
+  constexpr int TPC = NTH / 4;  // targets per CTA
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sm = reinterpret_cast<double *>(smem_raw);
   double *sup = sm;
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(128, 4) local_solve_small_kernel(const GskLoca
   // evaluation; no drift terms here that would need the coordinates themselves)
   constexpr bool UNIT = (VK == GSK_VARIO_SPHERICAL);
   const double cscale = UNIT ? a.vg.inv_r : 1.0;
-  for (int i = tid; i < 3 * a.nsup; i += 128) sup[i] = UNIT ? a.sup[i] * cscale : a.sup[i];
+  for (int i = tid; i < 3 * a.nsup; i += NTH) sup[i] = UNIT ? a.sup[i] * cscale : a.sup[i];
   __syncthreads();
   double *S = sm + nsup_pad + (size_t)grp * SK_GSZ;
   double *Sl = S + l;
@@ -244,16 +245,16 @@ __global__ void __launch_bounds__(128, 4) local_solve_small_kernel(const GskLoca
   }
 }
 
-template <int DIM, int VK>
+template <int DIM, int VK, int NTH = 256>
 inline cudaError_t launch_small_one(const GskLocalArgs &a, cudaStream_t st) {
   const int KC = (a.k + 3) / 4 * 4;
   const int nsup_pad = (3 * a.nsup + 3) & ~3;
-  const size_t smem = sizeof(double) * ((size_t)nsup_pad + 32 * (size_t)SK_GSZ);
-  auto kern = local_solve_small_kernel<DIM, VK>;
+  const size_t smem = sizeof(double) * ((size_t)nsup_pad + (NTH / 4) * (size_t)SK_GSZ);
+  auto kern = local_solve_small_kernel<DIM, VK, NTH>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
-  const unsigned grid = (unsigned)((a.count + 31) / 32);
-  kern<<<grid, 128, smem, st>>>(a, KC);
+  const unsigned grid = (unsigned)((a.count + NTH / 4 - 1) / (NTH / 4));
+  kern<<<grid, NTH, smem, st>>>(a, KC);
   return cudaGetLastError();
 }
 
