@@ -517,33 +517,28 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
 #pragma unroll
         for (int p = 0; p < c0; ++p) update(p);
       } else {
-        // runtime loop over the groups of A columns that share their first stored row pg, the group unrolled:
-        // colp[i] is element (row i, column p); base(p+1) − base(p) = RT − s_{p+1}, i.e. one constant stride inside
-        // a group and A less across the group boundary — a single add per column, no mask arithmetic
-        static_assert(W % A == 0, "panels must start on a column-group boundary");
+        // runtime loop with an incrementally advanced column pointer: colp[i] is element (row i, column p),
+        // base(p+1) − base(p) = LD − s_{p+1}. (Unrolling whole column groups saves the mask arithmetic but costs
+        // the 8-lane configuration registers: measured 5 % slower on C3b.)
         const double *colp = S;
-#pragma unroll 1
-        for (int pg = 0; pg < c0; pg += A) {
-          const int stride = LD - pg;
+#pragma unroll 2
+        for (int p = 0; p < c0; ++p) {
+          double piv[W];
 #pragma unroll
-          for (int pp = 0; pp < A; ++pp) {
-            double piv[W];
-#pragma unroll
-            for (int jj = 0; jj < W; jj += 2) {
-              const double2 t2 = *reinterpret_cast<const double2 *>(colp + c0 + jj);
-              piv[jj] = t2.x;
-              piv[jj + 1] = t2.y;
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-              if (SLOT_LIVE(r, c0)) {
-                const double own = GSK_ROW_OK(r) ? colp[ROW0(r) + l] : 0.0;
-#pragma unroll
-                for (int jj = 0; jj < W; ++jj) acc[r][jj] = fma(-own, piv[jj], acc[r][jj]);
-              }
-            }
-            colp += (pp + 1 < A) ? stride : stride - A;
+          for (int jj = 0; jj < W; jj += 2) {
+            const double2 t2 = *reinterpret_cast<const double2 *>(colp + c0 + jj);
+            piv[jj] = t2.x;
+            piv[jj + 1] = t2.y;
           }
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            if (SLOT_LIVE(r, c0)) {
+              const double own = GSK_ROW_OK(r) ? colp[ROW0(r) + l] : 0.0;
+#pragma unroll
+              for (int jj = 0; jj < W; ++jj) acc[r][jj] = fma(-own, piv[jj], acc[r][jj]);
+            }
+          }
+          colp += LD - ((p + 1) & ~(A - 1));
         }
       }
       // the W×W panel: pivots and row entries are exchanged by shuffles inside the group
@@ -612,20 +607,15 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
         for (int jj = 0; jj < W; ++jj) g[jj] = 0.0;
         const int i = ROW0(r) + l;
         const bool mine = i >= KC && i < KC + EPr;
-        const double *col = S;  // col[i] = element (row i, column p); same group-wise stride as in phase 4
-#pragma unroll 1
-        for (int pg = 0; pg < KC; pg += A) {
-          const int stride = LD - pg;
+        const double *col = S;  // col[i] = element (row i, column p)
+#pragma unroll 4
+        for (int p = 0; p < KC; ++p, col += LD - (p & ~(A - 1))) {
+          const double own = mine ? col[i] : 0.0;
 #pragma unroll
-          for (int pp = 0; pp < A; ++pp) {
-            const double own = mine ? col[i] : 0.0;
-#pragma unroll
-            for (int jj = 0; jj < W; jj += 2) {
-              const double2 t2 = *reinterpret_cast<const double2 *>(col + KC + cc + jj);
-              g[jj] = fma(own, t2.x, g[jj]);
-              g[jj + 1] = fma(own, t2.y, g[jj + 1]);
-            }
-            col += (pp + 1 < A) ? stride : stride - A;
+          for (int jj = 0; jj < W; jj += 2) {
+            const double2 t2 = *reinterpret_cast<const double2 *>(col + KC + cc + jj);
+            g[jj] = fma(own, t2.x, g[jj]);
+            g[jj + 1] = fma(own, t2.y, g[jj + 1]);
           }
         }
         if (mine) {
