@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -232,8 +233,11 @@ static int validate(gsk_ctx *ctx, const gsk_problem *p) {
   for (int d = 0; d < p->dim; ++d)
     if (!p->coords[d]) return fail(ctx, GSK_ERR_INVALID, "coords[d] is NULL for d < dim");
   if (p->grid_dims[0] > 0) {
-    for (int d = 0; d < p->dim; ++d)
+    for (int d = 0; d < p->dim; ++d) {
       if (p->grid_dims[d] < 1) return fail(ctx, GSK_ERR_INVALID, "grid_dims must be >= 1");
+      if (!(p->grid_spacing[d] > 0.0) || !std::isfinite(p->grid_spacing[d]) || !std::isfinite(p->grid_origin[d]))
+        return fail(ctx, GSK_ERR_INVALID, "grid_spacing must be finite and > 0, grid_origin finite");
+    }
   } else {
     if (p->n_points < 0) return fail(ctx, GSK_ERR_INVALID, "n_points must be >= 0");
     for (int d = 0; d < p->dim; ++d)
@@ -244,6 +248,14 @@ static int validate(gsk_ctx *ctx, const gsk_problem *p) {
   if (p->vario_kind < 0 || p->vario_kind > 2) return fail(ctx, GSK_ERR_UNSUPPORTED, "unknown variogram kind");
   if (!(p->vario_range > 0.0)) return fail(ctx, GSK_ERR_INVALID, "vario_range must be > 0");
   if (!(p->vario_sill > 0.0)) return fail(ctx, GSK_ERR_INVALID, "vario_sill must be > 0");
+  if (!(p->vario_nugget >= 0.0) || !(p->gaussian_nugget_eps >= 0.0))
+    return fail(ctx, GSK_ERR_INVALID, "vario_nugget and gaussian_nugget_eps must be >= 0");
+  if (!(p->vario_sill - p->vario_nugget - (p->vario_kind == GSK_VARIO_GAUSSIAN ? p->gaussian_nugget_eps : 0.0) > 0.0) ||
+      !std::isfinite(p->vario_sill) || !std::isfinite(p->vario_range))
+    return fail(ctx, GSK_ERR_INVALID, "the nugget must be below a finite sill, the range finite");
+  if (p->estimator == GSK_EST_SIMPLE && !std::isfinite(p->sk_mean))
+    return fail(ctx, GSK_ERR_INVALID, "sk_mean must be finite");
+  if (p->min_neighbors < 0) return fail(ctx, GSK_ERR_INVALID, "min_neighbors must be >= 0");
   if (p->estimator < 0 || p->estimator > 2) return fail(ctx, GSK_ERR_UNSUPPORTED, "unknown estimator");
   if (p->estimator == GSK_EST_UNIVERSAL && (p->uk_degree < 0 || p->uk_degree > 2))
     return fail(ctx, GSK_ERR_UNSUPPORTED, "uk_degree must be 0, 1 or 2");

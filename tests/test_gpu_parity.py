@@ -255,6 +255,15 @@ def test_invalid_arguments_are_rejected(gsk, ctx):
     bad.coords[0][3] = np.nan
     with pytest.raises(gsk.GskError, match="finite"):
         ctx.krige(bad)
+    bad = gsk.synth.config_spec("C2", scale=0.1)
+    bad.params["vario_nugget"] = 1.5                      # above the sill: no positive-definite covariance
+    with pytest.raises(gsk.GskError, match="nugget"):
+        ctx.krige(bad)
+    bad = gsk.synth.config_spec("C2", scale=0.1)
+    bad.grid_spacing[1] = 0.0
+    with pytest.raises(gsk.GskError, match="grid_spacing"):
+        ctx.krige(bad)
+    ctx.krige(spec)                                       # the context stays usable after rejected calls
 
 
 # ---- BASELINE-size sample sets (full n), parity on slabs of targets -------------------------------
