@@ -458,11 +458,14 @@ int gsk_oracle_krige(const gsk_problem *p, double *mean_out, double *var_out, in
   for (int64_t i = 0; i < n; i++)
     for (int d = 0; d < 3; d++) xyz[3 * i + d] = (d < dim) ? p->coords[d][i] : 0.0;
 
+  /* thread count of THIS call only (nthreads <= 0: all cores); the process-wide OpenMP setting is left alone */
 #ifdef _OPENMP
-  if (nthreads > 0) omp_set_num_threads(nthreads);
+  const int nt_call = nthreads > 0 ? nthreads : omp_get_max_threads();
 #else
+  const int nt_call = 1;
   (void)nthreads;
 #endif
+  (void)nt_call;
 
   if (p->max_neighbors == 0) {
     /* ---- exactsolve: fit once on all samples, predict everywhere (krig.jl:176-180) ---- */
@@ -473,7 +476,7 @@ int gsk_oracle_krige(const gsk_problem *p, double *mean_out, double *var_out, in
     int32_t *nb = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
     for (int64_t i = 0; i < n; i++) nb[i] = (int32_t)i;
     fit_system(p, &v, xyz, nb, (int)n, c, exps, &f);
-#pragma omp parallel
+#pragma omp parallel num_threads(nt_call)
     {
       double *rhs = (double *)malloc(sizeof(double) * (size_t)m);
       double *sol = (double *)malloc(sizeof(double) * (size_t)m);
@@ -497,7 +500,7 @@ int gsk_oracle_krige(const gsk_problem *p, double *mean_out, double *var_out, in
   kdtree_t *tree = (search_kind == GSK_ORACLE_SEARCH_KDTREE) ? kd_create(xyz, n, dim) : NULL;
   int use_ball = !(p->ball_radius != p->ball_radius);
   int mmax = k + c;
-#pragma omp parallel
+#pragma omp parallel num_threads(nt_call)
   {
     cand_t *best = (cand_t *)malloc(sizeof(cand_t) * (size_t)k);
     int32_t *nb = (int32_t *)malloc(sizeof(int32_t) * (size_t)k);
@@ -552,12 +555,15 @@ int gsk_oracle_search(const gsk_problem *p, int32_t *nneigh_out, int32_t *neigh_
     for (int d = 0; d < 3; d++) xyz[3 * i + d] = (d < p->dim) ? p->coords[d][i] : 0.0;
   kdtree_t *tree = (search_kind == GSK_ORACLE_SEARCH_KDTREE) ? kd_create(xyz, n, p->dim) : NULL;
   int use_ball = !(p->ball_radius != p->ball_radius);
+  /* thread count of THIS call only (nthreads <= 0: all cores); the process-wide OpenMP setting is left alone */
 #ifdef _OPENMP
-  if (nthreads > 0) omp_set_num_threads(nthreads);
+  const int nt_call = nthreads > 0 ? nthreads : omp_get_max_threads();
 #else
+  const int nt_call = 1;
   (void)nthreads;
 #endif
-#pragma omp parallel
+  (void)nt_call;
+#pragma omp parallel num_threads(nt_call)
   {
     cand_t *best = (cand_t *)malloc(sizeof(cand_t) * (size_t)k);
 #pragma omp for schedule(dynamic, 64)
