@@ -20,8 +20,10 @@ constexpr int sk_pad(int g) { return ((g & 15) == 4 || (g & 15) == 12) ? g : sk_
 constexpr int SK_GSZ = sk_pad(SK_STOR);  // ≡ 4 or 12 (mod 16) doubles: the groups of a warp spread over the banks
 
 // NTH threads per CTA (NTH/4 targets); 512 threads per SM either way — 256 measured 1 % ahead of 64/128, 512 8 % behind
-template <int DIM, int VK, int NTH = 256>
-__global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const GskLocalArgs a, const int KC) {
+// FULL: k = 20, the column count is a compile-time constant and the per-panel / per-column guards fold away
+template <int DIM, int VK, bool FULL, int NTH = 256>
+__global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const GskLocalArgs a, const int KC_arg) {
+  const int KC = FULL ? SK_KMAX : KC_arg;
   constexpr int G = 4, R = SK_R, W = 4, RT = SK_KMAX, A = 1, KM = SK_KMAX;
   constexpr int TPC = NTH / 4;  // targets per CTA
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -103,6 +105,17 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const
     ny[jj] = UNIT ? (rc.y - tc[1]) * cscale : rc.y;
     nz[jj] = UNIT ? (rc.z - tc[2]) * cscale : rc.z;
     nv[jj] = (a.es.kind == GSK_EST_SIMPLE) ? rc.w - a.es.sk_mean : rc.w;
+    // Unused slots (j >= nn: k not a multiple of 4, a ball that kept fewer, or a target that is not estimated)
+    // become samples of value 0 parked far away, each at its own place: every covariance with them evaluates to
+    // zero (1e-304 for the exp models) and their diagonal to C(0), so the rows decouple by themselves and neither
+    // the evaluation loops nor the fill need a validity select. 1e100 dwarfs any coordinate and its square is finite.
+    const int j = jj * G + l;
+    if (j >= nn) {
+      nx[jj] = 1e100 * (double)(j + 1);
+      ny[jj] = 0.0;
+      nz[jj] = 0.0;
+      nv[jj] = 0.0;
+    }
     bacc[jj] = 0.0;
   }
   // ---- phase 2: block-support RHS, q outermost (5 independent chains per lane) ----
@@ -112,14 +125,15 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const
   double yreg[KM];
   {
     const double inv_q = 1.0 / (double)a.nsup;
-    const bool ok_row = a.es.kind != GSK_EST_SIMPLE;
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) bacc[jj] *= inv_q;
+    // b and z are already zero in the unused slots; the ones row (Ordinary Kriging) ends at nn
+    const int n_ones = (l == 2 && a.es.kind != GSK_EST_SIMPLE) ? nn : 0;
 #pragma unroll
     for (int p = 0; p < KM; ++p) {
-      const double vb = __shfl_sync(0xffffffffu, bacc[p / G], gbase + (p % G)) * inv_q;
+      const double vb = __shfl_sync(0xffffffffu, bacc[p / G], gbase + (p % G));
       const double vz = __shfl_sync(0xffffffffu, nv[p / G], gbase + (p % G));
-      const bool valid_p = p < nn;
-      double v = (l == 0) ? vb : ((l == 1) ? vz : ((l == 2 && ok_row) ? 1.0 : 0.0));
-      yreg[p] = valid_p ? v : 0.0;
+      yreg[p] = (l == 0) ? vb : ((l == 1) ? vz : ((p < n_ones) ? 1.0 : 0.0));
     }
   }
   // ---- phase 4: covariance block into shared memory, column p rows >= p & ~3 (all static) ----
@@ -130,7 +144,6 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const
       const double xp = __shfl_sync(0xffffffffu, nx[p / G], gbase + (p % G));
       const double yp = __shfl_sync(0xffffffffu, ny[p / G], gbase + (p % G));
       const double zp = (DIM == 3) ? __shfl_sync(0xffffffffu, nz[p / G], gbase + (p % G)) : 0.0;
-      const bool valid_p = p < nn;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         if (r >= rlo) {
@@ -141,9 +154,9 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const
             const double dz = nz[r] - zp;
             d2 = fma(dz, dz, d2);
           }
-          double v = cov_fast<VK, UNIT>(vg, d2);
-          v = (i > p && i < nn) ? v : 0.0;
-          v = (i == p) ? (valid_p ? vg.sill : 1.0) : v;
+          // no selects: the diagonal is d2 == 0 → C(0) = sill, unused slots evaluate to zero by construction,
+          // and rows above the diagonal are neither stored here nor read by the factorisation
+          const double v = cov_fast<VK, UNIT>(vg, d2);
           if (r * G >= p || i >= p) Sl[col_off<RT, A>(p) - p + r * G] = v;
         }
       }
@@ -245,17 +258,22 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const
   }
 }
 
-template <int DIM, int VK, int NTH = 256>
-inline cudaError_t launch_small_one(const GskLocalArgs &a, cudaStream_t st) {
+template <int DIM, int VK, bool FULL, int NTH = 256>
+inline cudaError_t launch_small_full(const GskLocalArgs &a, cudaStream_t st) {
   const int KC = (a.k + 3) / 4 * 4;
   const int nsup_pad = (3 * a.nsup + 3) & ~3;
   const size_t smem = sizeof(double) * ((size_t)nsup_pad + (NTH / 4) * (size_t)SK_GSZ);
-  auto kern = local_solve_small_kernel<DIM, VK, NTH>;
+  auto kern = local_solve_small_kernel<DIM, VK, FULL, NTH>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   const unsigned grid = (unsigned)((a.count + NTH / 4 - 1) / (NTH / 4));
   kern<<<grid, NTH, smem, st>>>(a, KC);
   return cudaGetLastError();
+}
+
+template <int DIM, int VK>
+inline cudaError_t launch_small_one(const GskLocalArgs &a, cudaStream_t st) {
+  return (a.k + 3) / 4 * 4 == SK_KMAX ? launch_small_full<DIM, VK, true>(a, st) : launch_small_full<DIM, VK, false>(a, st);
 }
 
 }  // namespace gsk_local
