@@ -94,6 +94,18 @@ __device__ __forceinline__ double gsk_sqrt_pos(double u) {
   return fma(t, q, t);
 }
 
+// sqrt(u) for u >= 0 with sqrt(0) = 0 and no select: the seed's high word is capped below infinity on the integer
+// pipe (rsqrt(0) = +inf would give 0·inf), so u = 0 runs through the same arithmetic and yields t = 0·y = 0.
+__device__ __forceinline__ double gsk_sqrt_nonneg(double u) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(u));
+  y = __hiloint2double(min(__double2hiint(y), 0x7FE00000), 0);
+  const double t = u * y;
+  const double e = fma(-t, y, 1.0);
+  const double q = e * fma(0.375, e, 0.5);
+  return fma(t, q, t);
+}
+
 // exp(x) for x <= 0, branch-free (so that independent evaluations interleave): x = n·ln2 + f, |f| <= ln2/2,
 // degree-12 Taylor/Horner on f (truncation 2e-17 relative), scaled by 2^n through the exponent field.
 // Arguments below −700 are clamped (result ~1e-304, i.e. 0 at double precision for a covariance).
@@ -141,19 +153,21 @@ __device__ __forceinline__ bool gsk_lt_one(double d) { return __double2hiint(d) 
 
 // covariance from the squared distance, fast-path math (same formulas as gsk_cov)
 // UNIT: the coordinates were divided by the range beforehand, d2 is (h/r)² (spherical model only)
-template <int VK, bool UNIT = false>
+// NUG0: no nugget (sill == cs): C(0) then equals the model's own limit at h -> 0 and the d2 == 0 select goes away
+template <int VK, bool UNIT = false, bool NUG0 = false>
 __device__ __forceinline__ double cov_fast(const GskVario &v, double d2) {
   double c;
   if (VK == GSK_VARIO_GAUSSIAN) {
     c = v.cs * gsk_exp_neg(d2 * v.m3ir2);
   } else if (VK == GSK_VARIO_SPHERICAL) {
     const double u = UNIT ? d2 : d2 * v.inv_r2;
-    const double t = gsk_sqrt_pos(u);
+    const double t = NUG0 ? gsk_sqrt_nonneg(u) : gsk_sqrt_pos(u);
     c = gsk_lt_one(u) ? fma(t, fma(v.hcs, u, v.m15cs), v.cs) : 0.0;  // cs(1 − 1.5t + 0.5t³)
   } else {
-    const double h = gsk_is_pos(d2) ? gsk_sqrt_pos(d2) : 0.0;
+    const double h = NUG0 ? gsk_sqrt_nonneg(d2) : (gsk_is_pos(d2) ? gsk_sqrt_pos(d2) : 0.0);
     c = v.cs * gsk_exp_neg(v.m3ir * h);
   }
+  if (NUG0) return c;
   return gsk_is_pos(d2) ? c : v.sill;
 }
 
@@ -162,7 +176,7 @@ __device__ __forceinline__ double cov_fast(const GskVario &v, double d2) {
 // support that is small against the range (flag rhs_taylor, set on the host when 3·max|δ|/r <= 0.06) the
 // identity exp(−3h/r) = exp(−3h₀/r)·exp(−3(h−h₀)/r), |h − h₀| <= |δ|, needs ONE exp per neighbour and a degree-8
 // polynomial per support point (truncation <= 0.06⁹/9! = 3e-17 relative) instead of an exp per point.
-template <int VK, int DIM, int JM, bool UNIT = false>
+template <int VK, int DIM, int JM, bool UNIT = false, bool NUG0 = false>
 __device__ __forceinline__ void rhs_block_support(const GskLocalArgs &a, const GskVario &vg, const double *sup,
                                                   const double (&tc)[3], const double (&nx)[JM], const double (&ny)[JM],
                                                   const double (&nz)[JM], double (&bacc)[JM]) {
@@ -224,7 +238,7 @@ __device__ __forceinline__ void rhs_block_support(const GskLocalArgs &a, const G
         const double dz = uz - nz[jj];
         d2 = fma(dz, dz, d2);
       }
-      bacc[jj] += cov_fast<VK, UNIT>(vg, d2);
+      bacc[jj] += cov_fast<VK, UNIT, NUG0>(vg, d2);
     }
   }
 }

@@ -21,7 +21,8 @@ constexpr int SK_GSZ = sk_pad(SK_STOR);  // ≡ 4 or 12 (mod 16) doubles: the gr
 
 // NTH threads per CTA (NTH/4 targets); 512 threads per SM either way — 256 measured 1 % ahead of 64/128, 512 8 % behind
 // FULL: k = 20, the column count is a compile-time constant and the per-panel / per-column guards fold away
-template <int DIM, int VK, bool FULL, int NTH = 256>
+// NUG0: the variogram has no nugget (sill == cs; never true for the Gaussian model, which carries its 1e-6)
+template <int DIM, int VK, bool FULL, bool NUG0 = false, int NTH = 256>
 __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const GskLocalArgs a, const int KC_arg) {
   const int KC = FULL ? SK_KMAX : KC_arg;
   constexpr int G = 4, R = SK_R, W = 4, RT = SK_KMAX, A = 1, KM = SK_KMAX;
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const
   }
   // ---- phase 2: block-support RHS, q outermost (5 independent chains per lane) ----
   if (UNIT) tc[0] = tc[1] = tc[2] = 0.0;  // the centroid is the local origin
-  rhs_block_support<VK, DIM, R, UNIT>(a, vg, sup, tc, nx, ny, nz, bacc);
+  rhs_block_support<VK, DIM, R, UNIT, NUG0>(a, vg, sup, tc, nx, ny, nz, bacc);
   // ---- phase 3: extra rows into registers: lane 0 ← b, lane 1 ← z, lane 2 ← ones (OK), lane 3 ← 0 ----
   double yreg[KM];
   {
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const
           }
           // no selects: the diagonal is d2 == 0 → C(0) = sill, unused slots evaluate to zero by construction,
           // and rows above the diagonal are neither stored here nor read by the factorisation
-          const double v = cov_fast<VK, UNIT>(vg, d2);
+          const double v = cov_fast<VK, UNIT, NUG0>(vg, d2);
           if (r * G >= p || i >= p) Sl[col_off<RT, A>(p) - p + r * G] = v;
         }
       }
@@ -258,12 +259,12 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const
   }
 }
 
-template <int DIM, int VK, bool FULL, int NTH = 256>
+template <int DIM, int VK, bool FULL, bool NUG0 = false, int NTH = 256>
 inline cudaError_t launch_small_full(const GskLocalArgs &a, cudaStream_t st) {
   const int KC = (a.k + 3) / 4 * 4;
   const int nsup_pad = (3 * a.nsup + 3) & ~3;
   const size_t smem = sizeof(double) * ((size_t)nsup_pad + (NTH / 4) * (size_t)SK_GSZ);
-  auto kern = local_solve_small_kernel<DIM, VK, FULL, NTH>;
+  auto kern = local_solve_small_kernel<DIM, VK, FULL, NUG0, NTH>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   const unsigned grid = (unsigned)((a.count + NTH / 4 - 1) / (NTH / 4));
@@ -273,7 +274,9 @@ inline cudaError_t launch_small_full(const GskLocalArgs &a, cudaStream_t st) {
 
 template <int DIM, int VK>
 inline cudaError_t launch_small_one(const GskLocalArgs &a, cudaStream_t st) {
-  return (a.k + 3) / 4 * 4 == SK_KMAX ? launch_small_full<DIM, VK, true>(a, st) : launch_small_full<DIM, VK, false>(a, st);
+  if ((a.k + 3) / 4 * 4 != SK_KMAX) return launch_small_full<DIM, VK, false>(a, st);
+  if (VK != GSK_VARIO_GAUSSIAN && a.vg.sill == a.vg.cs) return launch_small_full<DIM, VK, true, VK != GSK_VARIO_GAUSSIAN>(a, st);
+  return launch_small_full<DIM, VK, true>(a, st);
 }
 
 }  // namespace gsk_local
