@@ -255,20 +255,24 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
 #define TD(sl) topd[(size_t)(sl) * NT + tid]
 #define TI(sl) topi[(size_t)(sl) * NT + tid]
             if (!HEAP) {
-              int p = (cnt < K) ? cnt : K - 1;
-              while (p > 0) {
-                double dp = TD(p - 1);
-                int ip = TI(p - 1);
-                if (d2 < dp || (d2 == dp && oi < ip)) {
-                  TD(p) = dp;
-                  TI(p) = ip;
-                  --p;
-                } else {
-                  break;
-                }
+              // sorted insertion with running pointers (slot stride NT is a compile-time constant, so the
+              // neighbouring slot is an immediate offset) and a branch-free (d², index) comparison
+              const int p0 = (cnt < K) ? cnt : K - 1;
+              double *pd = &TD(p0);
+              int *pi = &TI(p0);
+              double *const pd_first = &TD(0);
+              while (pd != pd_first) {
+                const double dp = pd[-NT];
+                const int ip = pi[-NT];
+                const bool before = (d2 < dp) | ((d2 == dp) & (oi < ip));
+                if (!before) break;
+                pd[0] = dp;
+                pi[0] = ip;
+                pd -= NT;
+                pi -= NT;
               }
-              TD(p) = d2;
-              TI(p) = oi;
+              pd[0] = d2;
+              pi[0] = oi;
               if (cnt < K) ++cnt;
               if (cnt == K) {
                 worst = TD(K - 1);
