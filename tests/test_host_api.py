@@ -164,3 +164,37 @@ def test_plain_c_host_compiles_against_the_header(gsk, tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)      # usage error, no compute call
     assert r.returncode == 2 and "usage" in r.stderr
+
+
+def test_julia_shim_struct_matches_the_header(gsk):
+    """julia/GSKrige.jl cannot run here (no julia binary); at least its `GskProblem` must list the fields of
+    include/gskrige.h's gsk_problem in the same order with types of the same width (ccall passes it by reference)."""
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    hdr = (root / "include" / "gskrige.h").read_text()
+    body = re.search(r"typedef struct gsk_problem \{(.*?)\} gsk_problem;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c_fields = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        m = re.match(r"(const double \*|double|int32_t|int64_t|uint32_t)\s*(.*)", decl)
+        assert m, decl
+        ctype = m.group(1).strip()
+        for name in m.group(2).split(","):
+            name = name.strip()
+            arr = re.match(r"(\w+)\[3\]", name)
+            c_fields.append((arr.group(1), ctype, 3) if arr else (name, ctype, 1))
+    jl = (root / "julia" / "GSKrige.jl").read_text()
+    jbody = re.search(r"struct GskProblem\n(.*?)\nend", jl, re.S).group(1)
+    width = {"Int32": "int32_t", "Int64": "int64_t", "UInt32": "uint32_t", "Float64": "double", "Ptr{Float64}": "const double *"}
+    j_fields = []
+    for line in jbody.splitlines():
+        name, typ = [t.strip() for t in line.split("::")]
+        tup = re.match(r"NTuple\{3,(.*)\}", typ)
+        j_fields.append((name, width[tup.group(1)], 3) if tup else (name, width[typ], 1))
+    assert j_fields == c_fields
+    # and the ctypes mirror used by the Python host agrees on the names and order as well
+    assert [f[0] for f in gsk._abi.GskProblem._fields_] == [f[0] for f in c_fields]
