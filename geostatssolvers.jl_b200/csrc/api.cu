@@ -98,7 +98,7 @@ extern "C" GSK_API int gsk_default_support(int dim, const double *spacing, doubl
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
-extern "C" GSK_API int gsk_create(gsk_ctx **out, int device_id) {
+extern "C" GSK_API int gsk_create(gsk_ctx **out, int device_id) try {
   if (!out) return fail(nullptr, GSK_ERR_INVALID, "gsk_create: out is NULL");
   *out = nullptr;
   int ndev = 0;
@@ -133,6 +133,10 @@ extern "C" GSK_API int gsk_create(gsk_ctx **out, int device_id) {
   }
   *out = ctx;
   return GSK_OK;
+} catch (const std::bad_alloc &) {  // no exception may cross the C ABI
+  return fail(nullptr, GSK_ERR_NOMEM, "gsk_create: out of host memory");
+} catch (const std::exception &e) {
+  return fail(nullptr, GSK_ERR_STATE, std::string("gsk_create: ") + e.what());
 }
 
 int gsk_buf(gsk_ctx *ctx, GskBufId id, size_t bytes, void **out) {
@@ -272,7 +276,7 @@ static int validate(gsk_ctx *ctx, const gsk_problem *p) {
   return GSK_OK;
 }
 
-extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) {
+extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) try {
   if (!ctx) return GSK_ERR_INVALID;
   int rc = validate(ctx, p);
   if (rc != GSK_OK) return rc;
@@ -377,6 +381,10 @@ extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) {
   ctx->prob.values = nullptr;
   ctx->planned = true;
   return GSK_OK;
+} catch (const std::bad_alloc &) {  // no exception may cross the C ABI
+  return fail(ctx, GSK_ERR_NOMEM, "gsk_plan: out of host memory");
+} catch (const std::exception &e) {
+  return fail(ctx, GSK_ERR_STATE, std::string("gsk_plan: ") + e.what());
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -405,7 +413,7 @@ static long long local_chunk_targets() {
 static int execute_impl(gsk_ctx *ctx, int64_t first, int64_t count, int32_t *d_nneigh, int32_t *d_neigh_idx);
 
 extern "C" GSK_API int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count, double *d_mean, double *d_var,
-                           int32_t *d_nneigh, int32_t *d_neigh_idx) {
+                           int32_t *d_nneigh, int32_t *d_neigh_idx) try {
   if (!ctx) return GSK_ERR_INVALID;
   if (!d_mean || !d_var) return fail(ctx, GSK_ERR_INVALID, "output buffers are NULL");
   ctx->out = GskOut{};
@@ -413,11 +421,15 @@ extern "C" GSK_API int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count, d
   ctx->out.mean[0] = d_mean;
   ctx->out.var[0] = d_var;
   return execute_impl(ctx, first, count, d_nneigh, d_neigh_idx);
+} catch (const std::bad_alloc &) {  // no exception may cross the C ABI
+  return fail(ctx, GSK_ERR_NOMEM, "gsk_execute: out of host memory");
+} catch (const std::exception &e) {
+  return fail(ctx, GSK_ERR_STATE, std::string("gsk_execute: ") + e.what());
 }
 
 extern "C" GSK_API int gsk_execute_peers(gsk_ctx *ctx, int64_t first, int64_t count, int n_peers,
                                  double *const *d_mean_peers, double *const *d_var_peers, int64_t out_offset,
-                                 int multicast, int32_t *d_nneigh, int32_t *d_neigh_idx) {
+                                 int multicast, int32_t *d_nneigh, int32_t *d_neigh_idx) try {
   if (!ctx) return GSK_ERR_INVALID;
   if (n_peers < 1 || n_peers > GSK_MAX_PEERS || !d_mean_peers || !d_var_peers)
     return fail(ctx, GSK_ERR_INVALID, "n_peers must be in [1, 8] with non-NULL pointer lists");
@@ -431,6 +443,10 @@ extern "C" GSK_API int gsk_execute_peers(gsk_ctx *ctx, int64_t first, int64_t co
     ctx->out.var[p] = d_var_peers[p] + out_offset;
   }
   return execute_impl(ctx, first, count, d_nneigh, d_neigh_idx);
+} catch (const std::bad_alloc &) {  // no exception may cross the C ABI
+  return fail(ctx, GSK_ERR_NOMEM, "gsk_execute_peers: out of host memory");
+} catch (const std::exception &e) {
+  return fail(ctx, GSK_ERR_STATE, std::string("gsk_execute_peers: ") + e.what());
 }
 
 static int execute_impl(gsk_ctx *ctx, int64_t first, int64_t count, int32_t *d_nneigh, int32_t *d_neigh_idx) {
@@ -582,7 +598,7 @@ extern "C" GSK_API int gsk_get_timing(const gsk_ctx *cctx, gsk_timing *out) {
 // one-shot host-buffer call: plan + execute + copies
 // ---------------------------------------------------------------------------------------------
 extern "C" GSK_API int gsk_krige(gsk_ctx *ctx, const gsk_problem *p, double *mean_out, double *var_out, int32_t *nneigh_out,
-                         int32_t *neigh_idx_out) {
+                         int32_t *neigh_idx_out) try {
   if (!ctx) return GSK_ERR_INVALID;
   if (!mean_out || !var_out) return fail(ctx, GSK_ERR_INVALID, "mean_out / var_out are NULL");
   int rc = gsk_plan(ctx, p);
@@ -640,6 +656,10 @@ extern "C" GSK_API int gsk_krige(gsk_ctx *ctx, const gsk_problem *p, double *mea
   GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   GSK_CUDA_CHECK(ctx, cudaGetLastError());
   return GSK_OK;
+} catch (const std::bad_alloc &) {  // no exception may cross the C ABI
+  return fail(ctx, GSK_ERR_NOMEM, "gsk_krige: out of host memory");
+} catch (const std::exception &e) {
+  return fail(ctx, GSK_ERR_STATE, std::string("gsk_krige: ") + e.what());
 }
 
 extern "C" GSK_API int gsk_measure_fp64_peak(gsk_ctx *ctx, double *dfma_tflops, double *dmma_tflops) {
@@ -658,7 +678,7 @@ std::vector<gsk_ctx *> g_multi_ctx;   // slot i serves piece i (re-created if th
 
 extern "C" GSK_API int gsk_krige_multi(const int *device_ids, int n_devices, const gsk_problem *p, double *mean_out,
                                        double *var_out, int32_t *nneigh_out, int32_t *neigh_idx_out, char *errbuf,
-                                       int errbuf_len) {
+                                       int errbuf_len) try {
   auto set_err = [&](const std::string &m) {
     if (errbuf && errbuf_len > 0) {
       strncpy(errbuf, m.c_str(), (size_t)errbuf_len - 1);
@@ -711,4 +731,10 @@ extern "C" GSK_API int gsk_krige_multi(const int *device_ids, int n_devices, con
       return rcs[i];
     }
   return GSK_OK;
+} catch (const std::exception &e) {  // no exception may cross the C ABI (std::thread, allocations)
+  if (errbuf && errbuf_len > 0) {
+    strncpy(errbuf, e.what(), (size_t)errbuf_len - 1);
+    errbuf[errbuf_len - 1] = 0;
+  }
+  return GSK_ERR_NOMEM;
 }
