@@ -15,7 +15,8 @@ import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
-LIB_PATH = PKG_DIR / "csrc" / "libgskrige.so"
+# GSKRIGE_LIB: development override (A/B of kernel variants built from other source states); not a fallback
+LIB_PATH = Path(os.environ.get("GSKRIGE_LIB") or PKG_DIR / "csrc" / "libgskrige.so")
 
 GSK_ABI_VERSION = 1
 VARIO_GAUSSIAN, VARIO_SPHERICAL, VARIO_EXPONENTIAL = 0, 1, 2

@@ -357,6 +357,7 @@ extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) try {
       for (int d = 0; d < 3; ++d) d2 += sup[(size_t)d * p->n_support + q] * sup[(size_t)d * p->n_support + q];
       dmax2 = std::max(dmax2, d2);
     }
+    ctx->sup_rmax = sqrt(dmax2);
     ctx->rhs_taylor = (p->vario_kind == GSK_VARIO_EXPONENTIAL && p->n_support > 1 &&
                        3.0 * sqrt(dmax2) / p->vario_range <= 0.06 && !getenv("GSK_NO_RHS_TAYLOR")) ? 1 : 0;
     GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -625,22 +626,32 @@ extern "C" GSK_API int gsk_krige(gsk_ctx *ctx, const gsk_problem *p, double *mea
   // The slab is computed in a few pieces; the device→host copies of a finished piece run on the side stream
   // while the next piece is being computed (they overlap only when the host buffers are page-locked).
   {
-    long long piece = count;
+    // piece boundaries: 40 / 30 / 20 / 10 % of the slab (rounded to whole rows or planes of a grid) — only the
+    // last piece's copies are exposed after the compute has finished, so it is the smallest
+    std::vector<long long> bounds{0, (long long)count};
     if (count >= (1ll << 19)) {
-      piece = (count + 3) / 4;
+      long long unit = 128;
       if (ctx->tg.is_grid) {
         const int dim = ctx->tg.dim;
-        const long long unit = (dim == 3) ? ctx->tg.gdim[0] * ctx->tg.gdim[1] * 4 : (dim == 2 ? ctx->tg.gdim[0] * 8 : 128);
-        if (unit <= piece) piece = (piece + unit - 1) / unit * unit;
+        unit = (dim == 3) ? ctx->tg.gdim[0] * ctx->tg.gdim[1] * 4 : (dim == 2 ? ctx->tg.gdim[0] * 8 : 128);
       }
+      bounds.clear();
+      bounds.push_back(0);
+      const double cum[3] = {0.4, 0.7, 0.9};
+      for (int i = 0; i < 3; ++i) {
+        long long b = (long long)(cum[i] * (double)count);
+        if (unit * 8 <= count) b = (b + unit - 1) / unit * unit;
+        b = std::min<long long>(b, count);
+        if (b > bounds.back()) bounds.push_back(b);
+      }
+      if (count > bounds.back()) bounds.push_back(count);
     }
-    int pi = 0;
-    for (long long off = 0; off < count; off += piece, ++pi) {
-      const long long cnt = std::min<long long>(piece, count - off);
+    for (size_t pi = 0; pi + 1 < bounds.size(); ++pi) {
+      const long long off = bounds[pi], cnt = bounds[pi + 1] - bounds[pi];
       rc = gsk_execute(ctx, first + off, cnt, d_mean + off, d_var + off, d_nn ? d_nn + off : nullptr,
                        d_idx ? d_idx + off * k : nullptr);
       if (rc != GSK_OK) return rc;
-      const int eb = pi & 1;
+      const int eb = (int)(pi & 1);
       GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_search[eb], ctx->stream));  // reused as a "piece done" marker
       GSK_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_search[eb], 0));
       GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(mean_out + off, d_mean + off, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2));

@@ -74,6 +74,7 @@ struct GskLocalArgs {
   const double4 *rec_orig;  // samples in original order: {x, y, z, value}
   const double *sup;        // support offsets [3][nsup] (device)
   int nsup;
+  double rhs_inr_lim2;      // spherical model: (1 − max|δ|/range)² (a bit less), or −1: a neighbour whose squared centroid distance in range units is below it has all its support points inside the range
   int rhs_taylor;           // exponential model with 3·max|δ|/range <= 0.06: one exp per neighbour + polynomial per support point
   int k;                    // clamped max neighbours
   int min_neighbors;
@@ -142,6 +143,7 @@ struct gsk_ctx {
   GskEstimator es{};
   int margin0[3] = {1, 1, 1};
   int rhs_taylor = 0;
+  double sup_rmax = 0.0;  // max |δ_q| of the block support
 
   // scratch that grows on demand
   int *d_nn = nullptr;

@@ -13,6 +13,10 @@ int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long 
   a.sup = ctx->d_sup;
   a.nsup = ctx->prob.n_support;
   a.rhs_taylor = ctx->rhs_taylor;
+  {
+    const double ds = ctx->sup_rmax / ctx->vg.range;
+    a.rhs_inr_lim2 = (ds < 1.0) ? (1.0 - ds) * (1.0 - ds) * (1.0 - 1e-12) : -1.0;
+  }
   a.k = ctx->prob.max_neighbors;
   a.min_neighbors = ctx->prob.min_neighbors;
   a.use_ball = !(ctx->prob.ball_radius != ctx->prob.ball_radius);

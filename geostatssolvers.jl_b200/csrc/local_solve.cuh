@@ -154,7 +154,8 @@ __device__ __forceinline__ bool gsk_lt_one(double d) { return __double2hiint(d) 
 // covariance from the squared distance, fast-path math (same formulas as gsk_cov)
 // UNIT: the coordinates were divided by the range beforehand, d2 is (h/r)² (spherical model only)
 // NUG0: no nugget (sill == cs): C(0) then equals the model's own limit at h -> 0 and the d2 == 0 select goes away
-template <int VK, bool UNIT = false, bool NUG0 = false>
+// INR (spherical): the caller guarantees h < range, the range select is dropped
+template <int VK, bool UNIT = false, bool NUG0 = false, bool INR = false>
 __device__ __forceinline__ double cov_fast(const GskVario &v, double d2) {
   double c;
   if (VK == GSK_VARIO_GAUSSIAN) {
@@ -162,7 +163,8 @@ __device__ __forceinline__ double cov_fast(const GskVario &v, double d2) {
   } else if (VK == GSK_VARIO_SPHERICAL) {
     const double u = UNIT ? d2 : d2 * v.inv_r2;
     const double t = NUG0 ? gsk_sqrt_nonneg(u) : gsk_sqrt_pos(u);
-    c = gsk_lt_one(u) ? fma(t, fma(v.hcs, u, v.m15cs), v.cs) : 0.0;  // cs(1 − 1.5t + 0.5t³)
+    c = fma(t, fma(v.hcs, u, v.m15cs), v.cs);  // cs(1 − 1.5t + 0.5t³)
+    if (!INR) c = gsk_lt_one(u) ? c : 0.0;
   } else {
     const double h = NUG0 ? gsk_sqrt_nonneg(d2) : (gsk_is_pos(d2) ? gsk_sqrt_pos(d2) : 0.0);
     c = v.cs * gsk_exp_neg(v.m3ir * h);
@@ -176,7 +178,7 @@ __device__ __forceinline__ double cov_fast(const GskVario &v, double d2) {
 // support that is small against the range (flag rhs_taylor, set on the host when 3·max|δ|/r <= 0.06) the
 // identity exp(−3h/r) = exp(−3h₀/r)·exp(−3(h−h₀)/r), |h − h₀| <= |δ|, needs ONE exp per neighbour and a degree-8
 // polynomial per support point (truncation <= 0.06⁹/9! = 3e-17 relative) instead of an exp per point.
-template <int VK, int DIM, int JM, bool UNIT = false, bool NUG0 = false>
+template <int VK, int DIM, int JM, bool UNIT = false, bool NUG0 = false, bool INR = false>
 __device__ __forceinline__ void rhs_block_support(const GskLocalArgs &a, const GskVario &vg, const double *sup,
                                                   const double (&tc)[3], const double (&nx)[JM], const double (&ny)[JM],
                                                   const double (&nz)[JM], double (&bacc)[JM]) {
@@ -238,7 +240,7 @@ __device__ __forceinline__ void rhs_block_support(const GskLocalArgs &a, const G
         const double dz = uz - nz[jj];
         d2 = fma(dz, dz, d2);
       }
-      bacc[jj] += cov_fast<VK, UNIT, NUG0>(vg, d2);
+      bacc[jj] += cov_fast<VK, UNIT, NUG0, INR>(vg, d2);
     }
   }
 }

@@ -121,21 +121,45 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const
   }
   // ---- phase 2: block-support RHS, q outermost (5 independent chains per lane) ----
   if (UNIT) tc[0] = tc[1] = tc[2] = 0.0;  // the centroid is the local origin
-  rhs_block_support<VK, DIM, R, UNIT, NUG0>(a, vg, sup, tc, nx, ny, nz, bacc);
-  // ---- phase 3: extra rows into registers: lane 0 ← b, lane 1 ← z, lane 2 ← ones (OK), lane 3 ← 0 ----
+  if (VK == GSK_VARIO_SPHERICAL) {
+    // warp-uniform fast path: every support point of every neighbour of the warp's targets lies inside the range
+    // (the coordinates are centroid-relative in range units here), so the range select is not needed
+    bool inr = true;
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      double d2c = fma(ny[jj], ny[jj], nx[jj] * nx[jj]);
+      if (DIM == 3) d2c = fma(nz[jj], nz[jj], d2c);
+      inr = inr && (d2c < a.rhs_inr_lim2);
+    }
+    if (__all_sync(0xffffffffu, inr)) rhs_block_support<VK, DIM, R, UNIT, NUG0, true>(a, vg, sup, tc, nx, ny, nz, bacc);
+    else rhs_block_support<VK, DIM, R, UNIT, NUG0, false>(a, vg, sup, tc, nx, ny, nz, bacc);
+  } else {
+    rhs_block_support<VK, DIM, R, UNIT, NUG0>(a, vg, sup, tc, nx, ny, nz, bacc);
+  }
+  // ---- phase 3: extra rows into registers: lane 0 ← b, lane 1 ← z, lane 2 ← ones (OK), lane 3 ← (unused).
+  //      Transposed through shared memory — the factor storage S is not written before phase 4: every lane stores
+  //      its 5 entries of the rows b, z, ones; lane l then reads row min(l, 2) with 10 LDS.128. (The shuffle
+  //      version cost 80 SHFL and as many selects per warp.) ----
   double yreg[KM];
   {
     const double inv_q = 1.0 / (double)a.nsup;
+    const bool ok_row = a.es.kind != GSK_EST_SIMPLE;
 #pragma unroll
-    for (int jj = 0; jj < R; ++jj) bacc[jj] *= inv_q;
-    // b and z are already zero in the unused slots; the ones row (Ordinary Kriging) ends at nn
-    const int n_ones = (l == 2 && a.es.kind != GSK_EST_SIMPLE) ? nn : 0;
-#pragma unroll
-    for (int p = 0; p < KM; ++p) {
-      const double vb = __shfl_sync(0xffffffffu, bacc[p / G], gbase + (p % G));
-      const double vz = __shfl_sync(0xffffffffu, nv[p / G], gbase + (p % G));
-      yreg[p] = (l == 0) ? vb : ((l == 1) ? vz : ((p < n_ones) ? 1.0 : 0.0));
+    for (int jj = 0; jj < R; ++jj) {
+      const int j = jj * G + l;
+      Sl[0 * KM + jj * G] = bacc[jj] * inv_q;            // zero in the unused slots by construction
+      Sl[1 * KM + jj * G] = nv[jj];                      // ditto
+      Sl[2 * KM + jj * G] = (ok_row && j < nn) ? 1.0 : 0.0;
     }
+    __syncwarp();
+    const double2 *row = reinterpret_cast<const double2 *>(S + (l < 2 ? l : 2) * KM);
+#pragma unroll
+    for (int i = 0; i < KM / 2; ++i) {
+      const double2 v = row[i];
+      yreg[2 * i] = v.x;
+      yreg[2 * i + 1] = v.y;
+    }
+    __syncwarp();  // phase 4 overwrites S
   }
   // ---- phase 4: covariance block into shared memory, column p rows >= p & ~3 (all static) ----
 #pragma unroll

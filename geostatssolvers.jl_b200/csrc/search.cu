@@ -23,6 +23,7 @@
 namespace {
 
 constexpr int NT = 128;       // targets (threads) per CTA
+constexpr int CB = 2;         // candidates whose loads and distances are issued together
 constexpr int SCAP_MAX = 1024;  // upper bound of staged records per chunk (32 KB)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -237,8 +238,8 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
         parity ^= 1u;
         if (active) {
           const int ns = hi - lo;
-          for (int s = 0; s < ns; ++s) {
-            const double4 rc = stage[s];
+          // squared distance with round-to-nearest mul/add and no FMA: bit-identical to the oracle
+          auto dist2 = [&](const double4 &rc) {
             double dx = tc[0] - rc.x;
             double d2 = __dmul_rn(dx, dx);
             if (DIM > 1) {
@@ -249,9 +250,12 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
               double dz = tc[2] - rc.z;
               d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
             }
-            if (d2 > worst) continue;
-            const int oi = (int)__double_as_longlong(rc.w);
-            if (d2 == worst && oi > worst_i) continue;
+            return d2;
+          };
+          auto consider = [&](const double d2, const double w) {
+            if (d2 > worst) return;
+            const int oi = (int)__double_as_longlong(w);
+            if (d2 == worst && oi > worst_i) return;
 #define TD(sl) topd[(size_t)(sl) * NT + tid]
 #define TI(sl) topi[(size_t)(sl) * NT + tid]
             if (!HEAP) {
@@ -322,6 +326,24 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
                 worst_i = TI(0);
               }
             }
+          };
+          // candidates in batches of CB: their broadcast loads and distance arithmetic are issued together (the
+          // loads cannot move above the previous candidate's shared-memory stores by themselves), the top-k
+          // updates then run in order
+          int s = 0;
+          for (; s + CB <= ns; s += CB) {
+            double4 rc[CB];
+            double dd[CB];
+#pragma unroll
+            for (int u = 0; u < CB; ++u) rc[u] = stage[s + u];
+#pragma unroll
+            for (int u = 0; u < CB; ++u) dd[u] = dist2(rc[u]);
+#pragma unroll
+            for (int u = 0; u < CB; ++u) consider(dd[u], rc[u].w);
+          }
+          for (; s < ns; ++s) {
+            const double4 rc = stage[s];
+            consider(dist2(rc), rc.w);
           }
         }
         __syncthreads();  // stage is overwritten by the next chunk

@@ -18,6 +18,8 @@ int gsk_oracle_search(const gsk_problem *p, int32_t *nneigh_out, int32_t *neigh_
 int gsk_oracle_uk_exponents(int degree, int dim, int32_t *out, int cap);
 int64_t gsk_oracle_num_targets(const gsk_problem *p);
 int gsk_oracle_threads(void);
+/* drops the searcher (packed coordinates + KD-tree) kept from the last local gsk_oracle_krige call */
+void gsk_oracle_clear_cache(void);
 #ifdef __cplusplus
 }
 #endif
