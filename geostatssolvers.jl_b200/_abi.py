@@ -18,19 +18,23 @@ REPO_ROOT = PKG_DIR.parent
 # GSKRIGE_LIB: development override (A/B of kernel variants built from other source states); not a fallback
 LIB_PATH = Path(os.environ.get("GSKRIGE_LIB") or PKG_DIR / "csrc" / "libgskrige.so")
 
-GSK_ABI_VERSION = 1
+GSK_ABI_VERSION = 2
 VARIO_GAUSSIAN, VARIO_SPHERICAL, VARIO_EXPONENTIAL = 0, 1, 2
 EST_SIMPLE, EST_ORDINARY, EST_UNIVERSAL = 0, 1, 2
-FLAG_CLAMP_VARIANCE, FLAG_SQRT_ROUNDTRIP = 1, 2
+FLAG_CLAMP_VARIANCE, FLAG_SQRT_ROUNDTRIP, FLAG_REUSE_PLAN = 1, 2, 4
 FLAGS_DEFAULT = 3
+SOLVER_KRIGING, SOLVER_IDW, SOLVER_LWR = 0, 1, 2
+LWR_WEIGHT_EXP3H2 = 0
 GSK_MAX_NEIGHBORS = 96
 GSK_MAX_SUPPORT = 125
+GSK_MAX_SUPPORT_GLOBAL = 65536
 
 ERRORS = {0: "ok", -1: "invalid argument", -2: "unsupported option", -3: "CUDA failure", -4: "out of memory",
           -5: "call-order violation"}
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
 
 
 class GskProblem(C.Structure):
@@ -63,6 +67,10 @@ class GskProblem(C.Structure):
         ("max_neighbors", C.c_int32),
         ("ball_radius", C.c_double),
         ("flags", C.c_uint32),
+        ("target_order", _lp),
+        ("solver", C.c_int32),
+        ("idw_exponent", C.c_double),
+        ("lwr_weightfun", C.c_int32),
     ]
 
 
@@ -91,7 +99,8 @@ class ProblemSpec:
     def __init__(self, *, coords, values, grid_dims=None, grid_origin=None, grid_spacing=None, points=None,
                  support=None, vario_kind=VARIO_GAUSSIAN, vario_range=1.0, vario_sill=1.0, vario_nugget=0.0,
                  gaussian_nugget_eps=1e-6, estimator=EST_ORDINARY, sk_mean=0.0, uk_degree=0, min_neighbors=1,
-                 max_neighbors=0, ball_radius=float("nan"), flags=FLAGS_DEFAULT, target_first=0, target_count=-1):
+                 max_neighbors=0, ball_radius=float("nan"), flags=FLAGS_DEFAULT, target_first=0, target_count=-1,
+                 target_order=None, solver=SOLVER_KRIGING, idw_exponent=1.0, lwr_weightfun=LWR_WEIGHT_EXP3H2):
         coords = [_as_f64(c) for c in coords]
         self.dim = len(coords)
         if not 1 <= self.dim <= 3:
@@ -123,9 +132,15 @@ class ProblemSpec:
                            vario_nugget=float(vario_nugget), gaussian_nugget_eps=float(gaussian_nugget_eps),
                            estimator=int(estimator), sk_mean=float(sk_mean), uk_degree=int(uk_degree),
                            min_neighbors=int(min_neighbors), max_neighbors=int(max_neighbors),
-                           ball_radius=float(ball_radius), flags=int(flags))
+                           ball_radius=float(ball_radius), flags=int(flags), solver=int(solver),
+                           idw_exponent=float(idw_exponent), lwr_weightfun=int(lwr_weightfun))
         self.target_first = int(target_first)
         self.target_count = int(target_count)
+        self.target_order = None
+        if target_order is not None:
+            self.target_order = np.ascontiguousarray(np.asarray(target_order, dtype=np.int64))
+            if self.target_order.shape != (self.n_targets,):
+                raise ValueError("target_order must list every target once")
 
     # -- derived -------------------------------------------------------------------
     @property
@@ -155,6 +170,8 @@ class ProblemSpec:
         if first is None:
             first, count = self.slab
         lin = np.arange(first, first + count, dtype=np.int64)
+        if self.target_order is not None:
+            lin = self.target_order[lin]
         if self.grid_dims is None:
             return [p[lin] for p in self.points]
         out, rem = [], lin
@@ -193,6 +210,7 @@ class ProblemSpec:
         p.n_support = int(self.support[0].shape[0])
         for k, v in self.params.items():
             setattr(p, k, v)
+        p.target_order = self.target_order.ctypes.data_as(_lp) if self.target_order is not None else None
         return p
 
 

@@ -358,6 +358,23 @@ extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) try {
       dmax2 = std::max(dmax2, d2);
     }
     ctx->sup_rmax = sqrt(dmax2);
+    // tensor-grid support with 3 offsets per axis, x fastest (what gsk_default_support produces for cells no larger
+    // than the range): the solve kernels then form the squared distances to the support points from per-axis squares
+    {
+      const int q = p->n_support;
+      int want = 1;
+      for (int d = 0; d < dim; ++d) want *= 3;
+      bool ok = (q == want);
+      for (int d = 0; d < 3 && ok; ++d) {
+        const int stride = (d == 0) ? 1 : (d == 1 ? 3 : 9);
+        for (int a = 0; a < 3; ++a) ctx->sup_ax[d][a] = (d < dim) ? sup[(size_t)d * q + (size_t)a * stride] : 0.0;
+        for (int i = 0; i < q && ok; ++i) {
+          const double expect = (d < dim) ? ctx->sup_ax[d][(i / stride) % 3] : 0.0;
+          ok = (sup[(size_t)d * q + i] == expect);
+        }
+      }
+      ctx->sup_tensor3 = ok ? 1 : 0;
+    }
     ctx->rhs_taylor = (p->vario_kind == GSK_VARIO_EXPONENTIAL && p->n_support > 1 &&
                        3.0 * sqrt(dmax2) / p->vario_range <= 0.06 && !getenv("GSK_NO_RHS_TAYLOR")) ? 1 : 0;
     GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -75,6 +75,8 @@ struct GskLocalArgs {
   const double *sup;        // support offsets [3][nsup] (device)
   int nsup;
   double rhs_inr_lim2;      // spherical model: (1 − max|δ|/range)² (a bit less), or −1: a neighbour whose squared centroid distance in range units is below it has all its support points inside the range
+  int sup_tensor3;          // the support is a tensor grid with 3 offsets per axis (the default for cells no larger than the range), x fastest
+  double sup_ax[3][3];      // its per-axis offsets: support point q = (kx, ky, kz), q = kx + 3·ky + 9·kz, sits at (sup_ax[0][kx], sup_ax[1][ky], sup_ax[2][kz])
   int rhs_taylor;           // exponential model with 3·max|δ|/range <= 0.06: one exp per neighbour + polynomial per support point
   int k;                    // clamped max neighbours
   int min_neighbors;
@@ -144,6 +146,8 @@ struct gsk_ctx {
   int margin0[3] = {1, 1, 1};
   int rhs_taylor = 0;
   double sup_rmax = 0.0;  // max |δ_q| of the block support
+  int sup_tensor3 = 0;    // see GskLocalArgs
+  double sup_ax[3][3] = {};
 
   // scratch that grows on demand
   int *d_nn = nullptr;

@@ -13,6 +13,9 @@ int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long 
   a.sup = ctx->d_sup;
   a.nsup = ctx->prob.n_support;
   a.rhs_taylor = ctx->rhs_taylor;
+  a.sup_tensor3 = ctx->sup_tensor3;
+  for (int d = 0; d < 3; ++d)
+    for (int i = 0; i < 3; ++i) a.sup_ax[d][i] = ctx->sup_ax[d][i];
   {
     const double ds = ctx->sup_rmax / ctx->vg.range;
     a.rhs_inr_lim2 = (ds < 1.0) ? (1.0 - ds) * (1.0 - ds) * (1.0 - 1e-12) : -1.0;
@@ -45,6 +48,12 @@ int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long 
   else if (rows(8) <= 112) err = gsk_local_launch_E(a, e, st);
   else {
     ctx->err = "max_neighbors too large for the local kernels";
+    return GSK_ERR_UNSUPPORTED;
+  }
+  if (err == cudaErrorInvalidConfiguration) {
+    (void)cudaGetLastError();
+    ctx->err = "this combination of max_neighbors, drift terms and n_support needs more shared memory per CTA than sm_100 "
+               "offers (227 KB): reduce n_support below 64, max_neighbors below 89 or the Universal Kriging degree";
     return GSK_ERR_UNSUPPORTED;
   }
   GSK_CUDA_CHECK(ctx, err);

@@ -29,6 +29,7 @@
 
 namespace gsk_local {
 
+constexpr size_t GSK_SMEM_OPTIN_MAX = 232448;  // opt-in shared memory per CTA on sm_100 (227 KB)
 
 template <int W>
 __host__ __device__ constexpr int col_align() { return W >= 8 ? 8 : 4; }
@@ -245,6 +246,104 @@ __device__ __forceinline__ void rhs_block_support(const GskLocalArgs &a, const G
   }
 }
 
+// Block-support right-hand side when the support is a 3-per-axis tensor grid (GskLocalArgs::sup_tensor3): the squared
+// distance from neighbour j to support point (kx, ky, kz) is sx[kx] + sy[ky] + sz[kz] with nine per-axis squares per
+// neighbour, i.e. 1⅓ additions per support point instead of three subtractions and three multiply-adds. Summation
+// order over q is the generic loop's (kx fastest). The Gaussian model separates completely:
+// Σ_q exp(−3(sx+sy+sz)/r²) = (Σ e^{−3sx/r²})(Σ e^{−3sy/r²})(Σ e^{−3sz/r²}) — 3·DIM exponentials per neighbour.
+// ax: the per-axis offsets (in range units when UNIT), tc: the target centroid (the origin when UNIT).
+template <int VK, int DIM, int JM, bool UNIT = false>
+__device__ __forceinline__ void rhs_tensor3(const GskLocalArgs &a, const GskVario &vg, const double (&ax)[3][3],
+                                            const double (&tc)[3], const double (&nx)[JM], const double (&ny)[JM],
+                                            const double (&nz)[JM], double (&bacc)[JM]) {
+  const bool nug0 = (VK != GSK_VARIO_GAUSSIAN) && (vg.sill == vg.cs);  // uniform: no C(0) discontinuity to honour
+#pragma unroll
+  for (int jj = 0; jj < JM; ++jj) {
+    double sx[3], sy[3], sz[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double ex = (tc[0] + ax[0][i]) - nx[jj], ey = (tc[1] + ax[1][i]) - ny[jj];
+      sx[i] = ex * ex;
+      sy[i] = ey * ey;
+      if (DIM == 3) {
+        const double ez = (tc[2] + ax[2][i]) - nz[jj];
+        sz[i] = ez * ez;
+      } else {
+        sz[i] = 0.0;
+      }
+    }
+    if (VK == GSK_VARIO_GAUSSIAN) {
+      double px = 0.0, py = 0.0, pz = 0.0;
+      int zx = 0, zy = 0, zz = 0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        px += gsk_exp_neg(sx[i] * vg.m3ir2);
+        py += gsk_exp_neg(sy[i] * vg.m3ir2);
+        if (DIM == 3) pz += gsk_exp_neg(sz[i] * vg.m3ir2);
+        zx += gsk_is_pos(sx[i]) ? 0 : 1;
+        zy += gsk_is_pos(sy[i]) ? 0 : 1;
+        zz += gsk_is_pos(sz[i]) ? 0 : 1;
+      }
+      // support points that sit exactly on the sample contribute C(0) = sill instead of cs
+      const int nzero = zx * zy * ((DIM == 3) ? zz : 1);
+      const double prod = (DIM == 3) ? px * py * pz : px * py;
+      bacc[jj] = fma(vg.cs, prod, (vg.sill - vg.cs) * (double)nzero);
+      continue;
+    }
+    double h0 = 0.0;
+    if (VK == GSK_VARIO_EXPONENTIAL && a.rhs_taylor) {
+      const double dx = tc[0] - nx[jj], dy = tc[1] - ny[jj];
+      double d2 = fma(dy, dy, dx * dx);
+      if (DIM == 3) {
+        const double dz = tc[2] - nz[jj];
+        d2 = fma(dz, dz, d2);
+      }
+      h0 = gsk_is_pos(d2) ? gsk_sqrt_pos(d2) : 0.0;
+    }
+    double acc = 0.0, zc = 0.0;
+#pragma unroll
+    for (int kz = 0; kz < (DIM == 3 ? 3 : 1); ++kz) {
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const double syz = (DIM == 3) ? sy[ky] + sz[kz] : sy[ky];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const double s = sx[kx] + syz;
+          if (VK == GSK_VARIO_SPHERICAL) {
+            const double u = UNIT ? s : s * vg.inv_r2;
+            const double t = gsk_sqrt_nonneg(u);
+            double c = fma(t, fma(vg.hcs, u, vg.m15cs), vg.cs);
+            c = gsk_lt_one(u) ? c : 0.0;
+            if (!nug0) c = gsk_is_pos(s) ? c : vg.sill;
+            acc += c;
+          } else if (a.rhs_taylor) {
+            const bool pos = gsk_is_pos(s);
+            const double h = gsk_sqrt_nonneg(s);
+            const double x = vg.m3ir * (h - h0);
+            double p = 2.48015873015873015873e-05;      // 1/8!
+            p = fma(p, x, 1.98412698412698412698e-04);  // 1/7!
+            p = fma(p, x, 1.38888888888888888889e-03);
+            p = fma(p, x, 8.33333333333333333333e-03);
+            p = fma(p, x, 4.16666666666666666667e-02);
+            p = fma(p, x, 1.66666666666666666667e-01);
+            p = fma(p, x, 0.5);
+            p = fma(p, x, 1.0);
+            p = fma(p, x, 1.0);
+            acc += pos ? p : 0.0;
+            zc += pos ? 0.0 : 1.0;
+          } else {
+            double c = vg.cs * gsk_exp_neg(vg.m3ir * gsk_sqrt_nonneg(s));
+            if (!nug0) c = gsk_is_pos(s) ? c : vg.sill;
+            acc += c;
+          }
+        }
+      }
+    }
+    if (VK == GSK_VARIO_EXPONENTIAL && a.rhs_taylor) acc = fma(vg.cs * gsk_exp_neg(vg.m3ir * h0), acc, vg.sill * zc);
+    bacc[jj] = acc;
+  }
+}
+
 // G lanes per target, R register row slots (R·G >= RS), W panel width, RS rows stored per column,
 // NT threads per CTA
 template <int G, int R, int W, int RS, int NT, int DIM, int VK>
@@ -269,11 +368,18 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
 #define GSK_ROW_OK(r) ((ROW0(r) >= 0) || (ROW0(r) + l >= 0))
 #define SLOT_LIVE(r, c) (ROW0(r) + G - 1 >= (c))          /* slot r still holds rows >= c */
 #define OWNER_SLOT(j) (BOTTOM_UP ? (RS - 1 - (j)) / G : (j) / G)
+  // One warp per target: the neighbour coordinates used for the covariances are taken relative to the target
+  // centroid and, for the spherical model, in units of the range (d² is then the polynomial's argument); the
+  // covariance block is filled pair by pair (see phase 3)
+  constexpr bool PAIRFILL = (G == 32);
+  constexpr bool UNITG = PAIRFILL && (VK == GSK_VARIO_SPHERICAL);
+  constexpr int CTAB = PAIRFILL ? ((KCMAX + 1) / 2 + 3) / 4 * 4 : 0;  // doubles holding the column-base table (ints)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sm = reinterpret_cast<double *>(smem_raw);
   double *sup = sm;  // [3][nsup]
   const int nsup_pad = (3 * a.nsup + 3) & ~3;
-  double *groups = sm + nsup_pad;
+  int *ctab = reinterpret_cast<int *>(sm + nsup_pad);  // element (row i, column c) of a packed factor sits at ctab[c] + i
+  double *groups = sm + nsup_pad + CTAB;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -300,7 +406,10 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
     if (nidx[jj] >= 0) nrec[jj] = a.rec_orig[nidx[jj]];
   }
 
-  for (int i = tid; i < 3 * a.nsup; i += CTA_THREADS) sup[i] = a.sup[i];
+  const double cscale = UNITG ? a.vg.inv_r : 1.0;
+  for (int i = tid; i < 3 * a.nsup; i += CTA_THREADS) sup[i] = UNITG ? a.sup[i] * cscale : a.sup[i];
+  if (PAIRFILL)
+    for (int c = tid; c < KCMAX; c += CTA_THREADS) ctab[c] = col_off<LD, A>(c) - (c & ~(A - 1));
   __syncthreads();
 
   double *S = groups + (size_t)grp * L.gsz;
@@ -349,6 +458,7 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
   // ---- phase 1+2: gather my neighbours (j = l, l+G, …) into registers; block-support RHS
   //      b_j = mean_q C(‖t + δ_q − x_j‖) with the q loop outermost so that the JM evaluations of a
   //      lane are independent (ILP); write the extra rows of column j ----
+  double cx[JM], cy[JM], cz[JM];  // covariance coordinates of my neighbours (PAIRFILL keeps them for phase 3)
   {
     double nx[JM], ny[JM], nz[JM], nv[JM], bacc[JM];
 #pragma unroll
@@ -357,13 +467,29 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
       const double4 rc = nrec[jj];
       nx[jj] = rc.x; ny[jj] = rc.y; nz[jj] = rc.z; nv[jj] = rc.w;
       bacc[jj] = 0.0;
+      // (relative to the centroid before scaling: scaling absolute coordinates would lose digits in the differences)
+      cx[jj] = UNITG ? (rc.x - tc[0]) * cscale : rc.x;
+      cy[jj] = UNITG ? (rc.y - tc[1]) * cscale : rc.y;
+      cz[jj] = UNITG ? (rc.z - tc[2]) * cscale : rc.z;
       if (j < KC) {
-        nbX[j] = rc.x;
-        nbY[j] = rc.y;
-        if (DIM == 3) nbZ[j] = rc.z;
+        nbX[j] = cx[jj];
+        nbY[j] = cy[jj];
+        if (DIM == 3) nbZ[j] = cz[jj];
       }
     }
-    rhs_block_support<VK, DIM, JM>(a, vg, sup, tc, nx, ny, nz, bacc);
+    {
+      const double tcz[3] = {UNITG ? 0.0 : tc[0], UNITG ? 0.0 : tc[1], UNITG ? 0.0 : tc[2]};  // UNITG: the centroid is the origin
+      if (PAIRFILL && a.sup_tensor3) {
+        double axs[3][3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) axs[d][i] = UNITG ? a.sup_ax[d][i] * cscale : a.sup_ax[d][i];
+        rhs_tensor3<VK, DIM, JM, UNITG>(a, vg, axs, tcz, cx, cy, cz, bacc);
+      } else {
+        rhs_block_support<VK, DIM, JM, UNITG>(a, vg, sup, tcz, cx, cy, cz, bacc);
+      }
+    }
     const double inv_q = 1.0 / (double)a.nsup;
     const int nextra = RT - KC;
 #pragma unroll
@@ -391,9 +517,62 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
   }
   __syncwarp();
 
-  // ---- phase 3: covariance block in place. Lane l owns rows i = r·G + l (coordinates in registers) and
-  //      walks the columns p; the R evaluations per column are independent ----
-  {
+  // ---- phase 3: covariance block in place.
+  if constexpr (PAIRFILL) {
+    // One warp per target: every unordered pair of neighbours is evaluated exactly once by a round-robin pairing.
+    // Lane l keeps rows i = l + 32·s (coordinates in registers, from phase 1); in round d it pairs each of them with
+    // row j = (i + d) mod KC, whose coordinates come from shared memory (consecutive lanes read consecutive entries).
+    // Rounds d = 1 … KC/2 − 1 cover the pairs at circular distance d from both sides, round KC/2 the antipodal pairs
+    // once: KC(KC−1)/2 evaluations, all lanes busy — the column-by-column fill (below, for G < 32) keeps the lanes of
+    // rows above the diagonal idle, 44 % of the work at KC = 64. Element (max, min) goes to ctab[min] + max.
+    const int M = KC, H = KC >> 1;
+#pragma unroll
+    for (int s2 = 0; s2 < JM; ++s2) {
+      const int i = l + 32 * s2;
+      if (i < KC) {
+        S[ctab[i] + i] = (i < nn) ? vg.sill : 1.0;                                 // diagonal (unused rows: identity)
+        for (int r2 = i & ~(A - 1); r2 < i; ++r2) S[ctab[i] + r2] = 0.0;          // in-block entries above it
+      }
+    }
+#pragma unroll 2
+    for (int d = 1; d < H; ++d) {
+#pragma unroll
+      for (int s2 = 0; s2 < JM; ++s2) {
+        const int i = l + 32 * s2;
+        const bool act = i < M;
+        int j = i + d;
+        j = (j >= M) ? j - M : j;
+        j = act ? j : 0;
+        const double dx = cx[s2] - nbX[j], dy = cy[s2] - nbY[j];
+        double d2 = fma(dy, dy, dx * dx);
+        if (DIM == 3) {
+          const double dz = cz[s2] - nbZ[j];
+          d2 = fma(dz, dz, d2);
+        }
+        double v = cov_fast<VK, UNITG>(vg, d2);
+        const int hi = max(i, j), lo = min(i, j);
+        v = (hi < nn) ? v : 0.0;
+        if (act) S[ctab[lo] + hi] = v;
+      }
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < JM; ++s2) {
+      const int i = l + 32 * s2;
+      const bool act = i < H;
+      const int j = act ? i + H : 0;
+      const double dx = cx[s2] - nbX[j], dy = cy[s2] - nbY[j];
+      double d2 = fma(dy, dy, dx * dx);
+      if (DIM == 3) {
+        const double dz = cz[s2] - nbZ[j];
+        d2 = fma(dz, dz, d2);
+      }
+      double v = cov_fast<VK, UNITG>(vg, d2);
+      v = (j < nn) ? v : 0.0;
+      if (act) S[ctab[i] + j] = v;
+    }
+  } else {
+    // Lane l owns rows i = r·G + l (coordinates in registers) and walks the columns p; the R evaluations per
+    // column are independent ----
     constexpr int RS_S = R;  // every slot may hold neighbour rows
     double xi[RS_S], yi[RS_S], zi[RS_S];
 #pragma unroll
@@ -719,7 +898,10 @@ inline cudaError_t launch_one(const GskLocalArgs &a, int e, cudaStream_t st) {
   constexpr int TPC = TPW * (CTA_THREADS / 32);
   Layout L = make_layout<G, R, W, RS, DIM>(a.k, e);
   int nsup_pad = (3 * a.nsup + 3) & ~3;
-  size_t smem = sizeof(double) * ((size_t)nsup_pad + (size_t)TPC * L.gsz);
+  constexpr int KCMAX = RS - W;
+  constexpr int CTAB = (G == 32) ? ((KCMAX + 1) / 2 + 3) / 4 * 4 : 0;  // column-base table of the pair fill (kernel: ctab)
+  size_t smem = sizeof(double) * ((size_t)nsup_pad + CTAB + (size_t)TPC * L.gsz);
+  if (smem > GSK_SMEM_OPTIN_MAX) return cudaErrorInvalidConfiguration;  // reported as GSK_ERR_UNSUPPORTED by the caller
   auto kern = local_solve_kernel<G, R, W, RS, NT, DIM, VK>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;

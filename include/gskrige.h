@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define GSK_ABI_VERSION 1
+#define GSK_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define GSK_API __attribute__((visibility("default")))
@@ -46,10 +46,27 @@ enum { GSK_VARIO_GAUSSIAN = 0, GSK_VARIO_SPHERICAL = 1, GSK_VARIO_EXPONENTIAL = 
 /* estimator — selection precedence is host logic, ref: src/ui.jl:40-50 (kriging_ui) */
 enum { GSK_EST_SIMPLE = 0, GSK_EST_ORDINARY = 1, GSK_EST_UNIVERSAL = 2 };
 
+/* estimation solver whose per-location loop runs. All three share searcher_ui (ref: src/ui.jl:11-32), the traversal
+ * and the centroid/search step; they differ in what is computed from the neighbours:
+ *   KRIGING  ref: src/estimation/krig.jl:166-234   outputs: mean, variance
+ *   IDW      ref: src/estimation/idw.jl:112-142    outputs: Σ w z / Σ w with w = 1/d^exponent (a zero distance returns that
+ *                                                   sample's value), and the distance to the nearest neighbour (`var_distance`)
+ *   LWR      ref: src/estimation/lwr.jl:113-146    outputs: weighted-least-squares plane evaluated at the target and
+ *                                                   ‖W X (XᵀWX)⁻¹ x₀‖ (`var_variance`), weights weightfun(d / max d) */
+enum { GSK_SOLVER_KRIGING = 0, GSK_SOLVER_IDW = 1, GSK_SOLVER_LWR = 2 };
+
+/* LWR weight functions (lwr.jl:58: the default is h -> exp(-3 h^2); arbitrary Julia closures cannot cross the ABI) */
+enum { GSK_LWR_WEIGHT_EXP3H2 = 0 };
+
 /* flags */
 enum {
   GSK_FLAG_CLAMP_VARIANCE = 1u << 0, /* σ² = max(0, σ²)  (GeoStatsModels predictvar)            */
   GSK_FLAG_SQRT_ROUNDTRIP = 1u << 1, /* σ² -> (sqrt σ²)²  (Normal(μ,√σ²) then var(), krig.jl:183,231) */
+  /* gsk_krige only: when the samples, support and parameters are byte-identical to those of the plan already resident
+   * in the context, skip the upload and the bin build / factorisation (the repeated solve(prob, krig) calls of the
+   * conditional-simulation callers, ref: src/simulation/fft.jl:112-126,184-188). Off by default: the library then
+   * never depends on what an earlier call was given. */
+  GSK_FLAG_REUSE_PLAN = 1u << 2,
   GSK_FLAGS_DEFAULT = (1u << 0) | (1u << 1)
 };
 
@@ -65,7 +82,9 @@ enum {
 
 /* limits of the local (maxneighbors) kernels */
 #define GSK_MAX_NEIGHBORS 96
-#define GSK_MAX_SUPPORT 125 /* block-support sub-sample points per target cell */
+#define GSK_MAX_SUPPORT 125 /* block-support points per cell kept in shared memory; larger supports (anisotropic cells,
+                              short ranges: up to GSK_MAX_SUPPORT_GLOBAL) are streamed from global memory */
+#define GSK_MAX_SUPPORT_GLOBAL 65536
 #define GSK_MAX_DRIFT_TERMS 10 /* C(3+2,2): universal kriging up to degree 2 in 3-D */
 
 /* ---- the problem description ------------------------------------------------------ */
@@ -116,6 +135,17 @@ typedef struct gsk_problem {
   double ball_radius;    /* NaN -> KNearestSearch; else KBallSearch: kNN then dist <= radius */
 
   uint32_t flags;
+
+  /* ---- ABI version 2 ---- */
+  /* Traversal order (ref: traverse(pdomain, path), krig.jl:179,204; idw.jl:111; lwr.jl:112). NULL = LinearPath.
+   * Otherwise target_order[j] (j < gsk_num_targets) is the 0-based linear index of the j-th visited target and the
+   * outputs are written in VISITING order, as the reference does (it maps over the path and never permutes back,
+   * krig.jl:179-183,204-231): out[j] belongs to target target_order[j]. The slab [target_first, +target_count)
+   * then counts positions of the path. */
+  const int64_t *target_order;
+  int32_t solver;        /* GSK_SOLVER_* (0 = Kriging) */
+  double idw_exponent;   /* IDW: `exponent` (> 0; idw.jl:56,96) */
+  int32_t lwr_weightfun; /* LWR: GSK_LWR_WEIGHT_* */
 } gsk_problem;
 
 typedef struct gsk_ctx gsk_ctx; /* opaque: one CUDA device, its stream, resident buffers */
@@ -171,6 +201,12 @@ GSK_API int gsk_execute(gsk_ctx *ctx, int64_t first, int64_t count,
 GSK_API int gsk_execute_peers(gsk_ctx *ctx, int64_t first, int64_t count, int n_peers,
                               double *const *d_mean_peers, double *const *d_var_peers, int64_t out_offset,
                               int multicast, int32_t *d_nneigh, int32_t *d_neigh_idx);
+/* Values-only update of the planned problem: same sample coordinates, same parameters, new `values` (length
+ * n_samples of the plan). This is what the conditional-simulation callers need between realisations (ref:
+ * src/simulation/fft.jl:184-188 solves the same EstimationProblem again with the unconditional realisation's values
+ * at the data locations). Bins, the neighbour lists of the last gsk_execute range (local path) and the factor
+ * L, L⁻¹ (global path; only Y_E's value column and G_EE are recomputed) stay resident. */
+GSK_API int gsk_update_values(gsk_ctx *ctx, const double *values, int64_t n_values);
 GSK_API int gsk_get_timing(const gsk_ctx *ctx, gsk_timing *out);
 /* when on, gsk_execute brackets every search / solve launch with CUDA events (and synchronises on them)
  * so that gsk_timing.ms_search / ms_solve are filled; off by default (no synchronisation in gsk_execute) */
@@ -185,7 +221,9 @@ GSK_API int64_t gsk_num_targets(const gsk_problem *prob);
 GSK_API int gsk_uk_exponents(int degree, int dim, int32_t *out, int out_capacity_terms);
 /* default block support of a grid cell: per axis
  * n = ceil(side / (min(range, min side)/3)), offsets (j/(n+1) − 1/2)·side, j = 1..n.
- * Writes x-fastest tensor-product offsets; returns n_support or a negative error */
+ * Writes x-fastest tensor-product offsets; returns n_support or a negative error. With off_x == NULL nothing is
+ * written and the count is returned (size the arrays with it: anisotropic cells or ranges shorter than the cell
+ * give more than 27 points; counts above GSK_MAX_SUPPORT_GLOBAL are GSK_ERR_UNSUPPORTED) */
 GSK_API int gsk_default_support(int dim, const double *spacing, double vario_range,
                         double *off_x, double *off_y, double *off_z, int capacity);
 /* measured FP64 peaks of the context's device (roofline denominators): a dependent-free
