@@ -10,13 +10,14 @@ and the CUDA sources (csrc/). No CPU fallback.
 from ._abi import (Context, GskError, ProblemSpec, krige_multi, default_support, default_support_py, load_library,  # noqa: F401
                    uk_exponents, EXPORTED_SYMBOLS, LIB_PATH,
                    VARIO_GAUSSIAN, VARIO_SPHERICAL, VARIO_EXPONENTIAL, EST_SIMPLE, EST_ORDINARY, EST_UNIVERSAL,
-                   FLAG_CLAMP_VARIANCE, FLAG_SQRT_ROUNDTRIP, FLAGS_DEFAULT, GSK_MAX_NEIGHBORS)
+                   FLAG_CLAMP_VARIANCE, FLAG_SQRT_ROUNDTRIP, FLAG_REUSE_PLAN, FLAGS_DEFAULT, GSK_MAX_NEIGHBORS,
+                   SOLVER_KRIGING, SOLVER_IDW, SOLVER_LWR)
 from .host import (CartesianGrid, EstimationProblem, Euclidean, ExponentialVariogram, ExternalDriftKriging,  # noqa: F401
-                   GaussianVariogram, GeoTable, K, KBallSearch, KNearestSearch, Kriging, KrigingSolver, LinearPath,
-                   MetricBall, MultiGridPath, NoUnits, OrdinaryKriging, PointSet, Quantities, RandomPath,
+                   GaussianVariogram, GeoTable, IDWSolver, K, KBallSearch, KNearestSearch, Kriging, KrigingSolver, LWRSolver,
+                   LinearPath, MetricBall, MultiGridPath, NoUnits, OrdinaryKriging, PointSet, Quantities, RandomPath,
                    SimpleKriging, SphericalVariogram, UniversalKriging, Unit, UnsupportedOption, approxsolve, asarray,
                    default_context, degC, elunit, embeddim, exactsolve, georef, kriging_ui, maxneighbors, nelements,
-                   preprocess, searcher_ui, solve, uadjust)
+                   preprocess, searcher_ui, solve, traverse, uadjust)
 from . import sharding, synth  # noqa: F401
 from .sharding import gather_slabs, slab_bounds  # noqa: F401
 

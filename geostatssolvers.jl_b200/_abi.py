@@ -260,6 +260,8 @@ def load_library(path: os.PathLike | None = None):
     lib.gsk_execute_peers.argtypes = [ctx, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                       C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
     lib.gsk_execute_peers.restype = C.c_int
+    lib.gsk_update_values.argtypes = [ctx, _dp, C.c_int64]
+    lib.gsk_update_values.restype = C.c_int
     lib.gsk_get_timing.argtypes = [ctx, C.POINTER(GskTiming)]
     lib.gsk_get_timing.restype = C.c_int
     lib.gsk_set_phase_timing.argtypes = [ctx, C.c_int]
@@ -281,7 +283,7 @@ def load_library(path: os.PathLike | None = None):
 
 EXPORTED_SYMBOLS = [
     "gsk_create", "gsk_destroy", "gsk_last_error", "gsk_set_stream", "gsk_synchronize", "gsk_krige", "gsk_krige_multi", "gsk_plan",
-    "gsk_execute", "gsk_execute_peers", "gsk_get_timing", "gsk_set_phase_timing", "gsk_num_targets", "gsk_uk_exponents", "gsk_default_support",
+    "gsk_execute", "gsk_execute_peers", "gsk_update_values", "gsk_get_timing", "gsk_set_phase_timing", "gsk_num_targets", "gsk_uk_exponents", "gsk_default_support",
     "gsk_measure_fp64_peak", "gsk_abi_version",
 ]
 
@@ -317,12 +319,14 @@ class Context:
             raise GskError(rc, msg.decode() if msg else "")
 
     # -- one-shot, host buffers ------------------------------------------------------
-    def krige(self, spec: ProblemSpec, want_neighbors: bool = False):
+    def krige(self, spec: ProblemSpec, want_neighbors: bool = False, want_nneigh: bool = False):
+        """One-shot call. ``want_nneigh``: also return the neighbour COUNT per target (4 B per target — what the host
+        needs to mark `missing`); ``want_neighbors``: also the count × k index lists (parity tests only)."""
         first, count = spec.slab
         mean = np.empty(count, dtype=np.float64)
         var = np.empty(count, dtype=np.float64)
         k = spec.params["max_neighbors"]
-        nneigh = np.empty(count, dtype=np.int32) if want_neighbors else None
+        nneigh = np.empty(count, dtype=np.int32) if (want_neighbors or want_nneigh) else None
         idx = np.empty((count, max(k, 1)), dtype=np.int32) if (want_neighbors and k > 0) else None
         ps = spec.c_struct()
         rc = self.lib.gsk_krige(self._h, C.byref(ps), mean.ctypes.data, var.ctypes.data,
@@ -331,6 +335,8 @@ class Context:
         self._check(rc)
         if want_neighbors:
             return mean, var, nneigh, idx
+        if want_nneigh:
+            return mean, var, nneigh
         return mean, var
 
     def krige_into(self, spec: ProblemSpec, mean: np.ndarray, var: np.ndarray):
@@ -342,6 +348,11 @@ class Context:
     def plan(self, spec: ProblemSpec):
         ps = spec.c_struct()
         self._check(self.lib.gsk_plan(self._h, C.byref(ps)))
+
+    def update_values(self, values):
+        """Values-only update of the planned problem (``gsk_update_values``): same coordinates, new sample values."""
+        v = _as_f64(values)
+        self._check(self.lib.gsk_update_values(self._h, _ptr(v), int(v.shape[0])))
 
     def execute(self, first, count, d_mean, d_var, d_nneigh=0, d_idx=0):
         """Device pointers (ints). Asynchronous on the context stream."""
@@ -412,16 +423,20 @@ def uk_exponents(degree: int, dim: int) -> np.ndarray:
 
 
 def default_support(spacing, vario_range: float):
-    """Block-support offsets of a grid cell via the library helper."""
+    """Block-support offsets of a grid cell via the library helper. Any size: the count is
+    queried first (anisotropic cells or ranges shorter than the cell give far more than 27 points)."""
     lib = load_library()
     dim = len(spacing)
     sp = _as_f64(spacing)
-    bufs = [np.zeros(GSK_MAX_SUPPORT) for _ in range(3)]
-    n = lib.gsk_default_support(dim, _ptr(sp), float(vario_range), _ptr(bufs[0]), _ptr(bufs[1]), _ptr(bufs[2]),
-                                GSK_MAX_SUPPORT)
+    n = lib.gsk_default_support(dim, _ptr(sp), float(vario_range), None, None, None, 0)
     if n < 0:
-        raise GskError(n, "gsk_default_support")
-    return [bufs[d][:n].copy() for d in range(dim)]
+        raise GskError(n, "gsk_default_support: the support of this cell size / range needs more than "
+                          f"{GSK_MAX_SUPPORT_GLOBAL} points")
+    bufs = [np.zeros(n) for _ in range(3)]
+    m = lib.gsk_default_support(dim, _ptr(sp), float(vario_range), _ptr(bufs[0]), _ptr(bufs[1]), _ptr(bufs[2]), n)
+    if m != n:
+        raise GskError(m, "gsk_default_support")
+    return [bufs[d] for d in range(dim)]
 
 
 def default_support_py(spacing, vario_range: float):

@@ -18,6 +18,8 @@ LIB = CSRC / "libgskrige.so"
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
          "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v", "-ccbin", "g++"]
+# development builds only (scripts/dev): e.g. GSK_NVCC_EXTRA="-DGSK_DEV_TUNABLES"
+FLAGS += os.environ.get("GSK_NVCC_EXTRA", "").split()
 
 
 def _newer(src: Path, dst: Path, deps) -> bool:

@@ -69,7 +69,7 @@ extern "C" GSK_API int gsk_uk_exponents(int degree, int dim, int32_t *out, int c
 // n = ceil(side / (min(range, min side)/3)) points at parametric positions j/(n+1), j = 1..n.
 extern "C" GSK_API int gsk_default_support(int dim, const double *spacing, double vario_range, double *ox, double *oy,
                                    double *oz, int cap) {
-  if (dim < 1 || dim > 3 || !spacing || !ox) return GSK_ERR_INVALID;
+  if (dim < 1 || dim > 3 || !spacing) return GSK_ERR_INVALID;
   double lmin = INFINITY;
   for (int d = 0; d < dim; ++d)
     if (spacing[d] > 0) lmin = std::min(lmin, spacing[d]);
@@ -81,6 +81,8 @@ extern "C" GSK_API int gsk_default_support(int dim, const double *spacing, doubl
     n[d] = std::max(1, (int)ceil(spacing[d] / step - 1e-12));
     tot *= n[d];
   }
+  if (tot > GSK_MAX_SUPPORT_GLOBAL) return GSK_ERR_UNSUPPORTED;
+  if (!ox) return (int)tot;  // count only: the caller sizes its arrays with it
   if (tot > cap) return GSK_ERR_INVALID;
   double *o[3] = {ox, oy, oz};
   int w = 0;
@@ -180,6 +182,9 @@ static void free_plan(gsk_ctx *ctx) {
   for (int d = 0; d < 3; ++d) ctx->d_pts[d] = nullptr;
   gsk_global_free(ctx);
   ctx->planned = false;
+  ctx->nbr_cached = false;
+  ctx->nbr_reuse = false;
+  ctx->key_valid = false;
 }
 
 extern "C" GSK_API void gsk_destroy(gsk_ctx *ctx) {
@@ -191,6 +196,8 @@ extern "C" GSK_API void gsk_destroy(gsk_ctx *ctx) {
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   cudaFree(ctx->d_nn);
   cudaFree(ctx->d_nbr);
+  cudaFree(ctx->d_nn_out);
+  cudaFree(ctx->d_nbr_out);
   cudaFree(ctx->d_mean);
   cudaFree(ctx->d_var);
   for (int i = 0; i < 6; ++i)
@@ -247,8 +254,29 @@ static int validate(gsk_ctx *ctx, const gsk_problem *p) {
     for (int d = 0; d < p->dim; ++d)
       if (p->n_points > 0 && !p->point_coords[d]) return fail(ctx, GSK_ERR_INVALID, "point_coords[d] is NULL");
   }
-  if (p->n_support < 1 || p->n_support > GSK_MAX_SUPPORT)
-    return fail(ctx, GSK_ERR_INVALID, "n_support must be in [1, GSK_MAX_SUPPORT]");
+  if (p->n_support < 1 || p->n_support > GSK_MAX_SUPPORT_GLOBAL)
+    return fail(ctx, GSK_ERR_INVALID, "n_support must be in [1, GSK_MAX_SUPPORT_GLOBAL]");
+  if (p->solver < GSK_SOLVER_KRIGING || p->solver > GSK_SOLVER_LWR) return fail(ctx, GSK_ERR_UNSUPPORTED, "unknown solver");
+  if (p->solver != GSK_SOLVER_KRIGING) {
+    // IDW / LWR: no variogram, estimator or block support; max_neighbors == 0 means every sample (idw.jl:93, lwr.jl:95)
+    if (p->solver == GSK_SOLVER_IDW && !(p->idw_exponent > 0.0 && std::isfinite(p->idw_exponent)))
+      return fail(ctx, GSK_ERR_INVALID, "exponent must be positive");  // idw.jl:96
+    if (p->solver == GSK_SOLVER_LWR && p->lwr_weightfun != GSK_LWR_WEIGHT_EXP3H2)
+      return fail(ctx, GSK_ERR_UNSUPPORTED, "only the default LWR weight function h -> exp(-3 h^2) crosses the C ABI");
+    if (p->min_neighbors < 0 || p->max_neighbors < 0) return fail(ctx, GSK_ERR_INVALID, "min/max_neighbors must be >= 0");
+    if (p->max_neighbors > GSK_MAX_NEIGHBORS)
+      return fail(ctx, GSK_ERR_UNSUPPORTED, "max_neighbors exceeds GSK_MAX_NEIGHBORS (pass 0 to use every sample)");
+    if (p->max_neighbors > p->n_samples)
+      return fail(ctx, GSK_ERR_INVALID, "max_neighbors must be clamped to n_samples by the host (ui.jl:16-23)");
+    if ((p->max_neighbors > 0 ? p->max_neighbors : p->n_samples) < p->min_neighbors)
+      return fail(ctx, GSK_ERR_INVALID, "invalid min/max number of neighbors");  // idw.jl:97, lwr.jl:98
+    if (p->max_neighbors > 0 && !(p->ball_radius != p->ball_radius) && !(p->ball_radius > 0.0))
+      return fail(ctx, GSK_ERR_INVALID, "ball_radius must be > 0 or NaN");
+    int64_t T = gsk_num_targets(p);
+    int64_t first = p->target_first, count = p->target_count < 0 ? T - first : p->target_count;
+    if (first < 0 || count < 0 || first + count > T) return fail(ctx, GSK_ERR_INVALID, "target slab out of range");
+    return GSK_OK;
+  }
   if (p->vario_kind < 0 || p->vario_kind > 2) return fail(ctx, GSK_ERR_UNSUPPORTED, "unknown variogram kind");
   if (!(p->vario_range > 0.0)) return fail(ctx, GSK_ERR_INVALID, "vario_range must be > 0");
   if (!(p->vario_sill > 0.0)) return fail(ctx, GSK_ERR_INVALID, "vario_sill must be > 0");
@@ -329,7 +357,37 @@ extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) try {
     tg.gorg[d] = (d < dim) ? p->grid_origin[d] : 0.0;
     tg.gsp[d] = (d < dim) ? p->grid_spacing[d] : 1.0;
   }
-  if (!tg.is_grid) {
+  if (p->target_order) {
+    // a traversal order (non-linear path): the targets become an explicit point list in VISITING order — the
+    // centroid of target_order[j] with the library's own centroid arithmetic — so that out[j] is the j-th visited
+    // target, as in the reference (krig.jl:179-183, 204-231). Block support still applies (grid cells).
+    const int64_t T = ctx->n_targets;
+    std::vector<double> pts[3];
+    for (int d = 0; d < dim; ++d) pts[d].resize((size_t)std::max<int64_t>(1, T));
+    for (int64_t j = 0; j < T; ++j) {
+      const int64_t lin = p->target_order[j];
+      if (lin < 0 || lin >= T) return fail(ctx, GSK_ERR_INVALID, "target_order entries must be in [0, gsk_num_targets)");
+      if (tg.is_grid) {
+        int64_t rem = lin;
+        for (int d = 0; d < dim; ++d) {
+          const int64_t c = rem % tg.gdim[d];
+          rem /= tg.gdim[d];
+          pts[d][(size_t)j] = tg.gorg[d] + ((double)c + 0.5) * tg.gsp[d];  // = gsk_cell_center (no contraction on the host)
+        }
+      } else {
+        for (int d = 0; d < dim; ++d) pts[d][(size_t)j] = p->point_coords[d][lin];
+      }
+    }
+    tg.is_grid = 0;
+    tg.npts = T;
+    for (int d = 0; d < dim; ++d) {
+      rc = gsk_buf(ctx, (GskBufId)(BUF_PTS0 + d), sizeof(double) * (size_t)std::max<int64_t>(1, T), (void **)&ctx->d_pts[d]);
+      if (rc != GSK_OK) return rc;
+      GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_pts[d], pts[d].data(), sizeof(double) * (size_t)T, cudaMemcpyHostToDevice, ctx->stream));
+      tg.pts[d] = ctx->d_pts[d];
+    }
+    GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // pts[] go out of scope
+  } else if (!tg.is_grid) {
     tg.npts = p->n_points;
     for (int d = 0; d < dim; ++d) {
       rc = gsk_buf(ctx, (GskBufId)(BUF_PTS0 + d), sizeof(double) * (size_t)std::max<int64_t>(1, p->n_points), (void **)&ctx->d_pts[d]);
@@ -346,6 +404,11 @@ extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) try {
     for (int d = 0; d < dim; ++d)
       if (p->support_offsets[d])
         for (int q = 0; q < p->n_support; ++q) sup[(size_t)d * p->n_support + q] = p->support_offsets[d][q];
+    // two copies: the offsets as given, and in units of the variogram range (the spherical kernels work in that frame
+    // and read supports too large for shared memory straight from here)
+    const size_t nq3 = sup.size();
+    sup.resize(2 * nq3);
+    for (size_t i = 0; i < nq3; ++i) sup[nq3 + i] = sup[i] * (1.0 / p->vario_range);
     rc = gsk_buf(ctx, BUF_SUP, sizeof(double) * sup.size(), (void **)&ctx->d_sup);
     if (rc != GSK_OK) return rc;
     GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_sup, sup.data(), sizeof(double) * sup.size(), cudaMemcpyHostToDevice,
@@ -376,13 +439,26 @@ extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) try {
       ctx->sup_tensor3 = ok ? 1 : 0;
     }
     ctx->rhs_taylor = (p->vario_kind == GSK_VARIO_EXPONENTIAL && p->n_support > 1 &&
-                       3.0 * sqrt(dmax2) / p->vario_range <= 0.06 && !getenv("GSK_NO_RHS_TAYLOR")) ? 1 : 0;
+                       3.0 * sqrt(dmax2) / p->vario_range <= 0.06 && !GSK_DEV_ENV("GSK_NO_RHS_TAYLOR")) ? 1 : 0;
     GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   }
 
   if (p->max_neighbors > 0) {
     rc = gsk_build_bins(ctx, p->coords[0], dim > 1 ? p->coords[1] : nullptr, dim > 2 ? p->coords[2] : nullptr,
                         p->values, p->n_samples, dim, p->max_neighbors);
+  } else if (p->solver != GSK_SOLVER_KRIGING) {
+    // IDW / LWR over every sample: only the {x, y, z, value} records are needed
+    const long long n = p->n_samples;
+    double4 *hrec = nullptr;
+    if ((rc = gsk_buf(ctx, BUF_REC_ORIG, sizeof(double4) * (size_t)n, (void **)&ctx->d_rec_orig)) != GSK_OK) return rc;
+    if ((rc = gsk_host_stage(ctx, sizeof(double4) * (size_t)n, (void **)&hrec)) != GSK_OK) return rc;
+    for (long long i = 0; i < n; ++i) {
+      hrec[i] = make_double4(p->coords[0][i], dim > 1 ? p->coords[1][i] : 0.0, dim > 2 ? p->coords[2][i] : 0.0, p->values[i]);
+      if (!std::isfinite(hrec[i].x) || !std::isfinite(hrec[i].y) || !std::isfinite(hrec[i].z))
+        return fail(ctx, GSK_ERR_INVALID, "sample coordinates must be finite");
+    }
+    GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_rec_orig, hrec, sizeof(double4) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   } else {
     rc = gsk_global_plan(ctx, p->coords[0], dim > 1 ? p->coords[1] : nullptr, dim > 2 ? p->coords[2] : nullptr,
                          p->values);
@@ -397,6 +473,7 @@ extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) try {
   // the host pointers of the problem are not kept
   for (int d = 0; d < 3; ++d) { ctx->prob.coords[d] = nullptr; ctx->prob.point_coords[d] = nullptr; ctx->prob.support_offsets[d] = nullptr; }
   ctx->prob.values = nullptr;
+  ctx->prob.target_order = nullptr;
   ctx->planned = true;
   return GSK_OK;
 } catch (const std::bad_alloc &) {  // no exception may cross the C ABI
@@ -417,15 +494,6 @@ static int ensure(gsk_ctx *ctx, void **buf, size_t *cap, size_t bytes) {
   if (e != cudaSuccess) return fail(ctx, GSK_ERR_NOMEM, std::string("device allocation failed: ") + cudaGetErrorString(e));
   *cap = bytes;
   return GSK_OK;
-}
-
-static long long local_chunk_targets() {
-  static long long v = 0;
-  if (v == 0) {
-    const char *s = getenv("GSK_CHUNK_TARGETS");
-    v = s ? std::max<long long>(1024, atoll(s)) : -1;  // -1: automatic
-  }
-  return v;
 }
 
 static int execute_impl(gsk_ctx *ctx, int64_t first, int64_t count, int32_t *d_nneigh, int32_t *d_neigh_idx);
@@ -476,15 +544,29 @@ static int execute_impl(gsk_ctx *ctx, int64_t first, int64_t count, int32_t *d_n
   double ms_search = 0.0, ms_solve = 0.0;
   GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
   int rc = GSK_OK;
+  const bool kriging = ctx->prob.solver == GSK_SOLVER_KRIGING;
+  // the per-location body that follows the search: Kriging (assemble + factor + solve) or the IDW / LWR epilogue
+  auto launch_body = [&](cudaStream_t st, long long f, long long c, const int *nn, const int *nbr, long long off) -> int {
+    if (kriging) return gsk_launch_local_solve(ctx, st, f, c, nn, nbr, off, &launches);
+    return gsk_launch_simple_solver(ctx, st, f, c, nn, nbr, off, nullptr, &launches);
+  };
   if (ctx->prob.max_neighbors == 0) {
-    rc = gsk_global_execute(ctx, first, count, d_nneigh, &launches);
+    if (kriging) rc = gsk_global_execute(ctx, first, count, d_nneigh, &launches);
+    else rc = gsk_launch_simple_solver(ctx, ctx->stream, first, count, nullptr, nullptr, 0, d_nneigh, &launches);
     if (rc != GSK_OK) return rc;
   } else if (!ctx->tg.is_grid && count > 0) {
     // explicit points: process the slab in bin-sorted order (spatially coherent CTAs), then scatter back
     const int k = ctx->prob.max_neighbors;
     int *perm = nullptr, *nn_s = nullptr, *nbr_s = nullptr;
     double *sx = nullptr, *sy = nullptr, *sz = nullptr, *ms = nullptr, *vs = nullptr;
-    if ((rc = gsk_points_sort(ctx, first, count, &perm, &sx, &sy, &sz)) != GSK_OK) return rc;
+    // after a values-only update the bin order and the neighbour lists of the same range are still valid
+    const bool reuse = ctx->nbr_reuse && ctx->nbr_cached && ctx->nbr_first == first && ctx->nbr_count == count && ctx->pt_perm;
+    if (reuse) {
+      perm = ctx->pt_perm; sx = ctx->pt_sx; sy = ctx->pt_sy; sz = ctx->pt_sz;
+    } else {
+      ctx->nbr_cached = false;
+      if ((rc = gsk_points_sort(ctx, first, count, &perm, &sx, &sy, &sz)) != GSK_OK) return rc;
+    }
     if ((rc = gsk_buf(ctx, BUF_PT_MEAN, sizeof(double) * (size_t)count, (void **)&ms)) != GSK_OK) return rc;
     if ((rc = gsk_buf(ctx, BUF_PT_VAR, sizeof(double) * (size_t)count, (void **)&vs)) != GSK_OK) return rc;
     if ((rc = gsk_buf(ctx, BUF_PT_NN, sizeof(int) * (size_t)count, (void **)&nn_s)) != GSK_OK) return rc;
@@ -498,12 +580,15 @@ static int execute_impl(gsk_ctx *ctx, int64_t first, int64_t count, int32_t *d_n
     ctx->out.mean[0] = ms;
     ctx->out.var[0] = vs;
     if (phase_timing) cudaEventRecord(ctx->ev[3], ctx->stream);
-    rc = gsk_launch_search(ctx, ctx->stream, 0, count, nn_s, nbr_s, &launches);
+    if (!reuse) rc = gsk_launch_search(ctx, ctx->stream, 0, count, nn_s, nbr_s, &launches);
     if (phase_timing) cudaEventRecord(ctx->ev[4], ctx->stream);
-    if (rc == GSK_OK) rc = gsk_launch_local_solve(ctx, ctx->stream, 0, count, nn_s, nbr_s, 0, &launches);
+    if (rc == GSK_OK) rc = launch_body(ctx->stream, 0, count, nn_s, nbr_s, 0);
     ctx->tg = tg_saved;
     ctx->out = out_saved;
     if (rc != GSK_OK) return rc;
+    ctx->nbr_cached = true;
+    ctx->nbr_first = first; ctx->nbr_count = count;
+    ctx->pt_perm = perm; ctx->pt_sx = sx; ctx->pt_sy = sy; ctx->pt_sz = sz;
     if (phase_timing) {
       cudaEventRecord(ctx->ev[5], ctx->stream);
       cudaEventSynchronize(ctx->ev[5]);
@@ -519,57 +604,41 @@ static int execute_impl(gsk_ctx *ctx, int64_t first, int64_t count, int32_t *d_n
   } else {
     const int k = ctx->prob.max_neighbors;
     // chunks of ~1M targets bound the neighbour-list scratch (4k+4 B per target); chunk edges are aligned
-    // to whole tile layers of the grid where that is cheap. GSK_OVERLAP=1 runs the search of chunk c+1 on
-    // a side stream while chunk c is solved (measured on B200: no gain — both kernels already fill the
-    // SMs and small chunks add tail effects — so it is off by default).
-    static const bool want_overlap = getenv("GSK_OVERLAP") != nullptr;
-    long long chunk = local_chunk_targets();
-    if (chunk <= 0) {
-      chunk = 1ll << 20;
-      if (ctx->tg.is_grid) {
-        const int dim = ctx->tg.dim;
-        long long unit = (dim == 3) ? ctx->tg.gdim[0] * ctx->tg.gdim[1] * 4 : (dim == 2 ? ctx->tg.gdim[0] * 8 : 128);
-        if (unit <= (1ll << 21)) chunk = (chunk + unit - 1) / unit * unit;
-      }
+    // to whole tile layers of the grid where that is cheap. (Running the search of chunk c+1 on a side stream while
+    // chunk c is solved was measured on B200 in round 1: no gain — both kernels already fill the SMs.)
+    long long chunk = 1ll << 20;
+    if (ctx->tg.is_grid) {
+      const int dim = ctx->tg.dim;
+      long long unit = (dim == 3) ? ctx->tg.gdim[0] * ctx->tg.gdim[1] * 4 : (dim == 2 ? ctx->tg.gdim[0] * 8 : 128);
+      if (unit <= (1ll << 21)) chunk = (chunk + unit - 1) / unit * unit;
     }
     chunk = std::min<long long>(chunk, std::max<long long>(count, 1));
-    const bool overlap = want_overlap && !phase_timing && count > chunk;
-    const int nbuf = overlap ? 2 : 1;
+    // Neighbour lists of the whole range are kept in the context's own scratch when they are at most 1 GiB: after a
+    // values-only update (gsk_update_values arms `nbr_reuse`) the next execute of the same range skips the search.
+    const bool keep = !d_nneigh && !d_neigh_idx && (size_t)count * (size_t)k * sizeof(int) <= ((size_t)1 << 30);
+    const bool reuse = keep && ctx->nbr_reuse && ctx->nbr_cached && ctx->nbr_first == first && ctx->nbr_count == count &&
+                       !ctx->pt_perm;
+    if (!reuse) ctx->nbr_cached = false;
+    const size_t scratch_targets = keep ? (size_t)count : (size_t)chunk;
     if (!d_nneigh) {
-      rc = ensure(ctx, (void **)&ctx->d_nn, &ctx->cap_nn, sizeof(int) * (size_t)chunk * nbuf);
+      rc = ensure(ctx, (void **)&ctx->d_nn, &ctx->cap_nn, sizeof(int) * scratch_targets);
       if (rc != GSK_OK) return rc;
     }
     if (!d_neigh_idx) {
-      rc = ensure(ctx, (void **)&ctx->d_nbr, &ctx->cap_nbr, sizeof(int) * (size_t)chunk * k * nbuf);
+      rc = ensure(ctx, (void **)&ctx->d_nbr, &ctx->cap_nbr, sizeof(int) * scratch_targets * k);
       if (rc != GSK_OK) return rc;
     }
-    if (overlap) {
-      GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-      GSK_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-    }
-    long long c = 0;
-    for (long long off = 0; off < count; off += chunk, ++c) {
+    for (long long off = 0; off < count; off += chunk) {
       const long long cnt = std::min<long long>(chunk, count - off);
-      const int b = (int)(c % nbuf);
-      int *nn = d_nneigh ? d_nneigh + off : ctx->d_nn + (size_t)b * chunk;
-      int *nbr = d_neigh_idx ? d_neigh_idx + off * k : ctx->d_nbr + (size_t)b * chunk * k;
-      if (overlap) {
-        // the scratch of parity b is free once the solve of chunk c-2 has read it
-        if (c >= 2) GSK_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_solve[b], 0));
-        rc = gsk_launch_search(ctx, ctx->stream2, first + off, cnt, nn, nbr, &launches);
-        if (rc != GSK_OK) return rc;
-        GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_search[b], ctx->stream2));
-        GSK_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_search[b], 0));
-        rc = gsk_launch_local_solve(ctx, ctx->stream, first + off, cnt, nn, nbr, off, &launches);
-        if (rc != GSK_OK) return rc;
-        GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_solve[b], ctx->stream));
-        continue;
-      }
+      int *nn = d_nneigh ? d_nneigh + off : ctx->d_nn + (keep ? (size_t)off : 0);
+      int *nbr = d_neigh_idx ? d_neigh_idx + off * k : ctx->d_nbr + (keep ? (size_t)off * k : 0);
       if (phase_timing) cudaEventRecord(ctx->ev[3], ctx->stream);
-      rc = gsk_launch_search(ctx, ctx->stream, first + off, cnt, nn, nbr, &launches);
-      if (rc != GSK_OK) return rc;
+      if (!reuse) {
+        rc = gsk_launch_search(ctx, ctx->stream, first + off, cnt, nn, nbr, &launches);
+        if (rc != GSK_OK) return rc;
+      }
       if (phase_timing) cudaEventRecord(ctx->ev[4], ctx->stream);
-      rc = gsk_launch_local_solve(ctx, ctx->stream, first + off, cnt, nn, nbr, off, &launches);
+      rc = launch_body(ctx->stream, first + off, cnt, nn, nbr, off);
       if (rc != GSK_OK) return rc;
       if (phase_timing) {
         cudaEventRecord(ctx->ev[5], ctx->stream);
@@ -580,6 +649,11 @@ static int execute_impl(gsk_ctx *ctx, int64_t first, int64_t count, int32_t *d_n
         ms_search += a;
         ms_solve += b2;
       }
+    }
+    if (keep && count > 0) {
+      ctx->nbr_cached = true;
+      ctx->nbr_first = first; ctx->nbr_count = count;
+      ctx->pt_perm = nullptr;
     }
   }
   GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -613,80 +687,211 @@ extern "C" GSK_API int gsk_get_timing(const gsk_ctx *cctx, gsk_timing *out) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// values-only update and the identity of the resident plan
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void set_values_kernel(double4 *rec, const double *v, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rec[i].w = v[i];
+}
+
+// 64-bit hash of an array of doubles (four interleaved FNV-style lanes; identity check, not cryptography)
+unsigned long long hash_doubles(const double *p, long long n, unsigned long long seed) {
+  unsigned long long h[4] = {seed ^ 0x9E3779B97F4A7C15ull, seed ^ 0xC2B2AE3D27D4EB4Full, seed ^ 0x165667B19E3779F9ull,
+                             seed ^ 0x27D4EB2F165667C5ull};
+  if (!p) return seed;
+  long long i = 0;
+  for (; i + 4 <= n; i += 4)
+    for (int l = 0; l < 4; ++l) {
+      unsigned long long b;
+      memcpy(&b, p + i + l, 8);
+      h[l] = (h[l] ^ b) * 0x100000001B3ull;
+      h[l] ^= h[l] >> 32;
+    }
+  for (; i < n; ++i) {
+    unsigned long long b;
+    memcpy(&b, p + i, 8);
+    h[0] = (h[0] ^ b) * 0x100000001B3ull;
+    h[0] ^= h[0] >> 32;
+  }
+  return h[0] ^ (h[1] * 3) ^ (h[2] * 5) ^ (h[3] * 7) ^ (unsigned long long)n;
+}
+
+// everything of the problem except the sample VALUES and the slab: scalars (pointers zeroed) + array hashes
+void problem_identity(const gsk_problem *p, gsk_problem *scalars, unsigned long long *geom, unsigned long long *vals) {
+  *scalars = *p;
+  for (int d = 0; d < 3; ++d) { scalars->coords[d] = nullptr; scalars->point_coords[d] = nullptr; scalars->support_offsets[d] = nullptr; }
+  scalars->values = nullptr;
+  scalars->target_order = nullptr;
+  scalars->target_first = 0;
+  scalars->target_count = 0;
+  scalars->flags &= ~(uint32_t)GSK_FLAG_REUSE_PLAN;
+  unsigned long long g = 0x51ED270B153A4D1Full;
+  const int64_t T = gsk_num_targets(p);
+  for (int d = 0; d < p->dim; ++d) {
+    g = hash_doubles(p->coords[d], p->n_samples, g + d);
+    g = hash_doubles(p->support_offsets[d], p->n_support, g + 8 + d);
+    if (p->grid_dims[0] == 0) g = hash_doubles(p->point_coords[d], p->n_points, g + 16 + d);
+  }
+  if (p->target_order) g = hash_doubles(reinterpret_cast<const double *>(p->target_order), T, g + 32);  // 8-byte words
+  else g ^= 0xABCDull;
+  *geom = g;
+  *vals = hash_doubles(p->values, p->n_samples, 0x7F4A7C15ull);
+}
+}  // namespace
+
+extern "C" GSK_API int gsk_update_values(gsk_ctx *ctx, const double *values, int64_t n_values) try {
+  if (!ctx) return GSK_ERR_INVALID;
+  if (!ctx->planned) return fail(ctx, GSK_ERR_STATE, "gsk_update_values called before gsk_plan");
+  if (!values || n_values != ctx->prob.n_samples)
+    return fail(ctx, GSK_ERR_INVALID, "gsk_update_values: values must hold n_samples of the planned problem");
+  GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  const long long n = n_values;
+  double *hst = nullptr, *dv = nullptr;
+  int rc;
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // the staging buffer may still feed an earlier copy
+  if ((rc = gsk_host_stage(ctx, sizeof(double) * (size_t)n, (void **)&hst)) != GSK_OK) return rc;
+  if ((rc = gsk_buf(ctx, BUF_VALS, sizeof(double) * (size_t)n, (void **)&dv)) != GSK_OK) return rc;
+  memcpy(hst, values, sizeof(double) * (size_t)n);
+  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(dv, hst, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  set_values_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_rec_orig, dv, n);
+  GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  if (ctx->prob.max_neighbors == 0 && ctx->prob.solver == GSK_SOLVER_KRIGING) {
+    if ((rc = gsk_global_update_values(ctx)) != GSK_OK) return rc;
+  }
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->nbr_reuse = true;  // the neighbour lists of the last execute stay valid: same coordinates
+  if (ctx->key_valid) ctx->key_vals = hash_doubles(values, n, 0x7F4A7C15ull);
+  return GSK_OK;
+} catch (const std::bad_alloc &) {  // no exception may cross the C ABI
+  return fail(ctx, GSK_ERR_NOMEM, "gsk_update_values: out of host memory");
+} catch (const std::exception &e) {
+  return fail(ctx, GSK_ERR_STATE, std::string("gsk_update_values: ") + e.what());
+}
+
+// ---------------------------------------------------------------------------------------------
 // one-shot host-buffer call: plan + execute + copies
 // ---------------------------------------------------------------------------------------------
-extern "C" GSK_API int gsk_krige(gsk_ctx *ctx, const gsk_problem *p, double *mean_out, double *var_out, int32_t *nneigh_out,
-                         int32_t *neigh_idx_out) try {
-  if (!ctx) return GSK_ERR_INVALID;
-  if (!mean_out || !var_out) return fail(ctx, GSK_ERR_INVALID, "mean_out / var_out are NULL");
-  int rc = gsk_plan(ctx, p);
-  if (rc != GSK_OK) return rc;
-  const int64_t T = ctx->n_targets;
-  const int64_t first = p->target_first;
-  const int64_t count = p->target_count < 0 ? T - first : p->target_count;
-  if (count == 0) return GSK_OK;
+static int krige_pieces(gsk_ctx *ctx, const gsk_problem *p, int64_t first, int64_t count, double *mean_out, double *var_out,
+                        int32_t *nneigh_out, int32_t *neigh_idx_out) {
   const int k = p->max_neighbors;
-  rc = ensure(ctx, (void **)&ctx->d_mean, &ctx->cap_out, sizeof(double) * 2 * (size_t)count);
+  int rc = ensure(ctx, (void **)&ctx->d_mean, &ctx->cap_out, sizeof(double) * 2 * (size_t)count);
   if (rc != GSK_OK) return rc;
   double *d_mean = ctx->d_mean, *d_var = ctx->d_mean + count;
   int *d_nn = nullptr, *d_idx = nullptr;
   if (nneigh_out) {
-    rc = ensure(ctx, (void **)&ctx->d_nn, &ctx->cap_nn, sizeof(int) * (size_t)count);
+    rc = ensure(ctx, (void **)&ctx->d_nn_out, &ctx->cap_nn_out, sizeof(int) * (size_t)count);
     if (rc != GSK_OK) return rc;
-    d_nn = ctx->d_nn;
+    d_nn = ctx->d_nn_out;
   }
   if (neigh_idx_out && k > 0) {
-    rc = ensure(ctx, (void **)&ctx->d_nbr, &ctx->cap_nbr, sizeof(int) * (size_t)count * k);
+    rc = ensure(ctx, (void **)&ctx->d_nbr_out, &ctx->cap_nbr_out, sizeof(int) * (size_t)count * k);
     if (rc != GSK_OK) return rc;
-    d_idx = ctx->d_nbr;
+    d_idx = ctx->d_nbr_out;
   }
-  // The slab is computed in a few pieces; the device→host copies of a finished piece run on the side stream
-  // while the next piece is being computed (they overlap only when the host buffers are page-locked).
-  {
-    // piece boundaries: 40 / 30 / 20 / 10 % of the slab (rounded to whole rows or planes of a grid) — only the
-    // last piece's copies are exposed after the compute has finished, so it is the smallest
-    std::vector<long long> bounds{0, (long long)count};
-    if (count >= (1ll << 19)) {
-      long long unit = 128;
-      if (ctx->tg.is_grid) {
-        const int dim = ctx->tg.dim;
-        unit = (dim == 3) ? ctx->tg.gdim[0] * ctx->tg.gdim[1] * 4 : (dim == 2 ? ctx->tg.gdim[0] * 8 : 128);
-      }
-      bounds.clear();
-      bounds.push_back(0);
-      const double cum[3] = {0.4, 0.7, 0.9};
-      for (int i = 0; i < 3; ++i) {
-        long long b = (long long)(cum[i] * (double)count);
-        if (unit * 8 <= count) b = (b + unit - 1) / unit * unit;
-        b = std::min<long long>(b, count);
-        if (b > bounds.back()) bounds.push_back(b);
-      }
-      if (count > bounds.back()) bounds.push_back(count);
+  // The slab is computed in pieces of 40 / 30 / 20 / 10 %: the device→host copies of a finished piece run on the side
+  // stream while the next piece is being computed (they overlap only when the host buffers are page-locked), and only
+  // the last, smallest piece's copies are exposed after the compute has finished. A request for the neighbour lists
+  // (parity tests) or explicit points runs as one piece.
+  long long bounds[5] = {0, count, count, count, count};
+  int npieces = 1;
+  if (count >= (1ll << 19) && ctx->tg.is_grid && !d_idx) {
+    const int dim = ctx->tg.dim;
+    const long long unit = (dim == 3) ? ctx->tg.gdim[0] * ctx->tg.gdim[1] * 4 : (dim == 2 ? ctx->tg.gdim[0] * 8 : 128);
+    const double cut[3] = {0.4, 0.7, 0.9};
+    npieces = 4;
+    for (int i = 0; i < 3; ++i) {
+      long long b = (long long)(cut[i] * (double)count);
+      if (unit <= count / 8) b = (b + unit - 1) / unit * unit;
+      bounds[i + 1] = std::min<long long>(std::max<long long>(b, bounds[i]), count);
     }
-    for (size_t pi = 0; pi + 1 < bounds.size(); ++pi) {
-      const long long off = bounds[pi], cnt = bounds[pi + 1] - bounds[pi];
-      rc = gsk_execute(ctx, first + off, cnt, d_mean + off, d_var + off, d_nn ? d_nn + off : nullptr,
-                       d_idx ? d_idx + off * k : nullptr);
-      if (rc != GSK_OK) return rc;
-      const int eb = (int)(pi & 1);
-      GSK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_search[eb], ctx->stream));  // reused as a "piece done" marker
-      GSK_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_search[eb], 0));
-      GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(mean_out + off, d_mean + off, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2));
-      GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(var_out + off, d_var + off, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2));
-      if (d_nn)
-        GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(nneigh_out + off, d_nn + off, sizeof(int) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2));
-      if (d_idx)
-        GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(neigh_idx_out + off * k, d_idx + off * k, sizeof(int) * (size_t)cnt * k, cudaMemcpyDeviceToHost, ctx->stream2));
-    }
-    ctx->timing.targets = count;
+    bounds[4] = count;
   }
-  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream2));
-  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  // from here on every error path drains both streams first: copies into the caller's (possibly page-locked) host
+  // buffers may be in flight, and the caller is free to release them as soon as this function returns
+  auto drain = [&](int code) {
+    cudaStreamSynchronize(ctx->stream2);
+    cudaStreamSynchronize(ctx->stream);
+    return code;
+  };
+  for (int pi = 0; pi < npieces; ++pi) {
+    const long long off = bounds[pi], cnt = bounds[pi + 1] - bounds[pi];
+    if (cnt <= 0) continue;
+    rc = gsk_execute(ctx, first + off, cnt, d_mean + off, d_var + off, d_nn ? d_nn + off : nullptr,
+                     d_idx ? d_idx + off * k : nullptr);
+    if (rc != GSK_OK) return drain(rc);
+    const int eb = pi & 1;
+    cudaError_t ce = cudaEventRecord(ctx->ev_search[eb], ctx->stream);  // "piece done" marker
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stream2, ctx->ev_search[eb], 0);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(mean_out + off, d_mean + off, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(var_out + off, d_var + off, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2);
+    if (ce == cudaSuccess && d_nn)
+      ce = cudaMemcpyAsync(nneigh_out + off, d_nn + off, sizeof(int) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2);
+    if (ce == cudaSuccess && d_idx)
+      ce = cudaMemcpyAsync(neigh_idx_out + off * k, d_idx + off * k, sizeof(int) * (size_t)cnt * k, cudaMemcpyDeviceToHost, ctx->stream2);
+    if (ce != cudaSuccess) {
+      ctx->err = std::string("gsk_krige: result copy failed: ") + cudaGetErrorString(ce);
+      return drain(GSK_ERR_CUDA);
+    }
+  }
+  ctx->timing.targets = count;
+  cudaError_t ce = cudaStreamSynchronize(ctx->stream2);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+  if (ce == cudaSuccess) ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    ctx->err = std::string("gsk_krige: ") + cudaGetErrorString(ce);
+    return GSK_ERR_CUDA;
+  }
   return GSK_OK;
+}
+
+extern "C" GSK_API int gsk_krige(gsk_ctx *ctx, const gsk_problem *p, double *mean_out, double *var_out, int32_t *nneigh_out,
+                         int32_t *neigh_idx_out) try {
+  if (!ctx) return GSK_ERR_INVALID;
+  if (!mean_out || !var_out) return fail(ctx, GSK_ERR_INVALID, "mean_out / var_out are NULL");
+  int rc = GSK_OK;
+  bool planned_here = true;
+  if (p && (p->flags & GSK_FLAG_REUSE_PLAN) && p->abi_version == GSK_ABI_VERSION) {
+    // same problem as the resident plan? then nothing is uploaded or rebuilt; same problem with other VALUES (the
+    // conditional-simulation callers, fft.jl:184-188)? then only the values go up and bins / neighbour lists /
+    // L and L⁻¹ stay. The flag is opt-in: without it the library never depends on what an earlier call was given.
+    rc = validate(ctx, p);
+    if (rc != GSK_OK) return rc;
+    gsk_problem sc;
+    unsigned long long geom = 0, vals = 0;
+    problem_identity(p, &sc, &geom, &vals);
+    if (ctx->planned && ctx->key_valid && geom == ctx->key_geom && memcmp(&sc, &ctx->key_prob, sizeof(sc)) == 0) {
+      if (vals != ctx->key_vals) {
+        rc = gsk_update_values(ctx, p->values, p->n_samples);
+        if (rc != GSK_OK) return rc;
+      } else {
+        ctx->nbr_reuse = true;
+      }
+      ctx->timing.ms_plan = 0.0;
+      planned_here = false;
+    } else {
+      rc = gsk_plan(ctx, p);
+      if (rc != GSK_OK) return rc;
+      ctx->key_prob = sc;
+      ctx->key_geom = geom;
+      ctx->key_vals = vals;
+      ctx->key_valid = true;
+    }
+  } else {
+    rc = gsk_plan(ctx, p);
+    if (rc != GSK_OK) return rc;
+  }
+  (void)planned_here;
+  const int64_t T = ctx->n_targets;
+  const int64_t first = p->target_first;
+  const int64_t count = p->target_count < 0 ? T - first : p->target_count;
+  if (count == 0) return GSK_OK;
+  return krige_pieces(ctx, p, first, count, mean_out, var_out, nneigh_out, neigh_idx_out);
 } catch (const std::bad_alloc &) {  // no exception may cross the C ABI
+  if (ctx) { cudaStreamSynchronize(ctx->stream2); cudaStreamSynchronize(ctx->stream); }
   return fail(ctx, GSK_ERR_NOMEM, "gsk_krige: out of host memory");
 } catch (const std::exception &e) {
+  if (ctx) { cudaStreamSynchronize(ctx->stream2); cudaStreamSynchronize(ctx->stream); }
   return fail(ctx, GSK_ERR_STATE, std::string("gsk_krige: ") + e.what());
 }
 
@@ -742,17 +947,27 @@ extern "C" GSK_API int gsk_krige_multi(const int *device_ids, int n_devices, con
   const int k = p->max_neighbors;
   std::vector<int> rcs(n_devices, GSK_OK);
   std::vector<std::thread> workers;
-  for (int i = 0; i < n_devices; ++i) {
-    workers.emplace_back([&, i]() {
-      const int64_t lo = count * i / n_devices, hi = count * (i + 1) / n_devices;
-      gsk_problem pi = *p;
-      pi.target_first = first + lo;
-      pi.target_count = hi - lo;
-      rcs[i] = gsk_krige(g_multi_ctx[i], &pi, mean_out + lo, var_out + lo, nneigh_out ? nneigh_out + lo : nullptr,
-                         (neigh_idx_out && k > 0) ? neigh_idx_out + lo * k : nullptr);
-    });
+  workers.reserve((size_t)n_devices);
+  bool spawn_failed = false;
+  for (int i = 0; i < n_devices && !spawn_failed; ++i) {
+    try {
+      workers.emplace_back([&, i]() {
+        const int64_t lo = count * i / n_devices, hi = count * (i + 1) / n_devices;
+        gsk_problem pi = *p;
+        pi.target_first = first + lo;
+        pi.target_count = hi - lo;
+        rcs[i] = gsk_krige(g_multi_ctx[i], &pi, mean_out + lo, var_out + lo, nneigh_out ? nneigh_out + lo : nullptr,
+                           (neigh_idx_out && k > 0) ? neigh_idx_out + lo * k : nullptr);
+      });
+    } catch (const std::exception &) {
+      spawn_failed = true;  // joinable threads must be joined before anything else (std::terminate otherwise)
+    }
   }
   for (auto &w : workers) w.join();
+  if (spawn_failed) {
+    set_err("gsk_krige_multi: could not start a worker thread");
+    return GSK_ERR_NOMEM;
+  }
   for (int i = 0; i < n_devices; ++i)
     if (rcs[i] != GSK_OK) {
       set_err(gsk_last_error(g_multi_ctx[i]));

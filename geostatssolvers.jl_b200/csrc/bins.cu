@@ -126,8 +126,8 @@ int gsk_build_bins(gsk_ctx *ctx, const double *hx, const double *hy, const doubl
   }
   // cells sized for ~occ samples each (k/4…k/2 per cell, capped)
   // tunables (development): GSK_BIN_OCC_DIV (samples per cell = k / div), GSK_MARGIN_FACTOR
-  static const double occ_div = getenv("GSK_BIN_OCC_DIV") ? atof(getenv("GSK_BIN_OCC_DIV")) : 24.0;
-  static const double margin_factor = getenv("GSK_MARGIN_FACTOR") ? atof(getenv("GSK_MARGIN_FACTOR")) : 1.0;
+  static const double occ_div = GSK_DEV_ENV("GSK_BIN_OCC_DIV") ? atof(GSK_DEV_ENV("GSK_BIN_OCC_DIV")) : 24.0;
+  static const double margin_factor = GSK_DEV_ENV("GSK_MARGIN_FACTOR") ? atof(GSK_DEV_ENV("GSK_MARGIN_FACTOR")) : 1.0;
   double occ = std::min(8.0, std::max(1.0, k / occ_div));
   int live = 0;
   double vol = 1.0;
@@ -139,7 +139,7 @@ int gsk_build_bins(gsk_ctx *ctx, const double *hx, const double *hy, const doubl
   // number m of cells just covers it (cell = 1.02·r0/m; m = 3 in 2-D, 2 in 3-D, 4 in 1-D ⇒ ≈ k/28, k/33, k/8
   // samples per cell). The first block a tile scans then reaches r0 without overshooting by up to a cell —
   // measured on k = 64, 3-D: search 7.4 → 4.0 ms per 1e6 targets against the fixed-occupancy rule.
-  if (!getenv("GSK_BIN_OCC_DIV") && live > 0 && vol > 0.0) {
+  if (!GSK_DEV_ENV("GSK_BIN_OCC_DIV") && live > 0 && vol > 0.0) {
     const double dens0 = (double)n / vol;
     const double cd0 = (live <= 1) ? 2.0 : (live == 2 ? M_PI : 4.0 * M_PI / 3.0);
     const double r00 = pow((double)k / (dens0 * cd0), 1.0 / live);

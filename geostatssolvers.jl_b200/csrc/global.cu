@@ -670,6 +670,20 @@ int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const doub
   return GSK_OK;
 }
 
+// new sample values in rec_orig (gsk_update_values): only E's value column changes, hence Y_E = L⁻¹E and G_EE
+int gsk_global_update_values(gsk_ctx *ctx) {
+  GlobalPlan *g = ctx->gplan;
+  if (!g) { ctx->err = "global plan missing"; return GSK_ERR_STATE; }
+  cudaStream_t st = ctx->stream;
+  const long long np = g->np;
+  GArgs ga{ctx->d_rec_orig, g->n, np, ctx->vg, ctx->prob.dim};
+  build_e_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(ga, ctx->es, g->E);
+  linv_times_e_kernel<<<(unsigned)((np + 7) / 8), 256, 0, st>>>(g->X, np, np, g->E, g->ne, g->YE);
+  gram_ee_kernel<<<1, 256, 0, st>>>(g->YE, np, g->ne, g->GEE);
+  GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  return GSK_OK;
+}
+
 int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, int *d_nn, int *launches) {
   GlobalPlan *g = ctx->gplan;
   if (!g) { ctx->err = "global plan missing"; return GSK_ERR_STATE; }

@@ -7,6 +7,15 @@
 
 #include "../../include/gskrige.h"
 
+// Development tunables (bin occupancy, staging capacity, kernel selection) exist only in builds made with
+// -DGSK_DEV_TUNABLES (scripts/dev A/B runs). The product library reads no environment variable.
+#ifdef GSK_DEV_TUNABLES
+#include <stdlib.h>
+#define GSK_DEV_ENV(name) getenv(name)
+#else
+#define GSK_DEV_ENV(name) ((const char *)nullptr)
+#endif
+
 #define GSK_CUDA_CHECK(ctx, expr)                                                        \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \
@@ -73,6 +82,7 @@ struct GskLocalArgs {
   GskEstimator es;
   const double4 *rec_orig;  // samples in original order: {x, y, z, value}
   const double *sup;        // support offsets [3][nsup] (device)
+  const double *sup_unit;   // the same in units of the variogram range
   int nsup;
   double rhs_inr_lim2;      // spherical model: (1 − max|δ|/range)² (a bit less), or −1: a neighbour whose squared centroid distance in range units is below it has all its support points inside the range
   int sup_tensor3;          // the support is a tensor grid with 3 offsets per axis (the default for cells no larger than the range), x fastest
@@ -115,7 +125,7 @@ struct GlobalPlan;  // global.cu
 enum GskBufId {
   BUF_REC_ORIG, BUF_REC_SORTED, BUF_CELL_START, BUF_SUP, BUF_PTS0, BUF_PTS1, BUF_PTS2, BUF_CELL_OF, BUF_COUNTS,
   BUF_G_A, BUF_G_X, BUF_G_DINV, BUF_G_E, BUF_G_YE, BUF_G_GEE, BUF_G_BM, BUF_G_PARTIAL, BUF_PEAK,
-  BUF_PT_CELL, BUF_PT_COUNTS, BUF_PT_PERM, BUF_PT_X, BUF_PT_Y, BUF_PT_Z, BUF_PT_MEAN, BUF_PT_VAR, BUF_PT_NN, BUF_PT_NBR, BUF_COUNT
+  BUF_PT_CELL, BUF_PT_COUNTS, BUF_PT_PERM, BUF_PT_X, BUF_PT_Y, BUF_PT_Z, BUF_PT_MEAN, BUF_PT_VAR, BUF_PT_NN, BUF_PT_NBR, BUF_VALS, BUF_COUNT
 };
 
 struct gsk_ctx {
@@ -155,6 +165,21 @@ struct gsk_ctx {
   size_t cap_nn = 0, cap_nbr = 0;
   double *d_mean = nullptr, *d_var = nullptr;
   size_t cap_out = 0;
+  int *d_nn_out = nullptr, *d_nbr_out = nullptr;  // gsk_krige: neighbour counts / lists requested by the caller
+  size_t cap_nn_out = 0, cap_nbr_out = 0;
+
+  // neighbour lists kept from the last local gsk_execute (same plan, same target range): a values-only update
+  // (gsk_update_values) then skips the search — and, for explicit points, the bin sort — of the next call
+  bool nbr_cached = false;
+  bool nbr_reuse = false;  // armed by gsk_update_values, cleared by gsk_plan
+  long long nbr_first = -1, nbr_count = -1;
+  int *pt_perm = nullptr;
+  double *pt_sx = nullptr, *pt_sy = nullptr, *pt_sz = nullptr;
+
+  // identity of the resident plan for gsk_krige's GSK_FLAG_REUSE_PLAN: the scalar fields and hashes of the arrays
+  bool key_valid = false;
+  gsk_problem key_prob{};
+  unsigned long long key_geom = 0, key_vals = 0;
 
   GlobalPlan *gplan = nullptr;
 
@@ -179,6 +204,9 @@ int gsk_build_bins(gsk_ctx *ctx, const double *hx, const double *hy, const doubl
 // search.cu
 int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long count, int *d_nn, int *d_nbr,
                       int *launches);
+// estim.cu: the IDW / LWR per-location bodies on the neighbour lists (or on all samples when k == 0)
+int gsk_launch_simple_solver(gsk_ctx *ctx, cudaStream_t st, long long first, long long count, const int *d_nn,
+                             const int *d_nbr, long long out_off, int *d_nn_out, int *launches);
 // local_solve*.cu
 int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long long count, const int *d_nn,
                            const int *d_nbr, long long out_off, int *launches);
@@ -186,6 +214,7 @@ int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long 
 int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const double *hz, const double *hv);
 int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, int *d_nn, int *launches);
 void gsk_global_free(gsk_ctx *ctx);
+int gsk_global_update_values(gsk_ctx *ctx);  // rec_orig carries new values: rebuild E, Y_E, G_EE (L, L⁻¹ stay)
 // points.cu
 int gsk_points_sort(gsk_ctx *ctx, long long first, long long count, int **perm, double **sx, double **sy, double **sz);
 int gsk_points_unscatter(gsk_ctx *ctx, const int *perm, long long count, const double *ms, const double *vs,
@@ -200,6 +229,41 @@ int gsk_peak_measure(gsk_ctx *ctx, double *dfma, double *dmma);
 // target centroid: origin + (i + 0.5)·spacing, no FMA (bit-identical to the oracle)
 __device__ __forceinline__ double gsk_cell_center(double org, double sp, long long i) {
   return __dadd_rn(org, __dmul_rn((double)i + 0.5, sp));
+}
+
+// centroid of target `lin` (grid: x-fastest linear index; explicit points otherwise)
+__device__ __forceinline__ void gsk_target_center(const GskTargets &tg, long long lin, double (&tc)[3]) {
+  tc[0] = tc[1] = tc[2] = 0.0;
+  if (tg.is_grid) {
+    long long rem = lin;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (d < tg.dim) {
+        const long long c = rem % tg.gdim[d];
+        rem /= tg.gdim[d];
+        tc[d] = gsk_cell_center(tg.gorg[d], tg.gsp[d], c);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      if (d < tg.dim) tc[d] = tg.pts[d][lin];
+  }
+}
+
+// squared Euclidean distance exactly as the search kernel and the oracle form it: ((dx·dx)+(dy·dy))+(dz·dz), no FMA
+__device__ __forceinline__ double gsk_dist2_exact(int dim, const double (&tc)[3], const double4 &r) {
+  const double dx = tc[0] - r.x;
+  double d2 = __dmul_rn(dx, dx);
+  if (dim > 1) {
+    const double dy = tc[1] - r.y;
+    d2 = __dadd_rn(d2, __dmul_rn(dy, dy));
+  }
+  if (dim > 2) {
+    const double dz = tc[2] - r.z;
+    d2 = __dadd_rn(d2, __dmul_rn(dz, dz));
+  }
+  return d2;
 }
 
 // covariance C(h) = sill − γ(h) from the squared distance (d2 == 0 → sill)

@@ -2,6 +2,7 @@
 #include <stdlib.h>
 
 #include "local_solve_small.cuh"
+#include "local_solve_wpt.cuh"
 
 int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long long count, const int *d_nn,
                            const int *d_nbr, long long out_off, int *launches) {
@@ -11,6 +12,7 @@ int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long 
   a.es = ctx->es;
   a.rec_orig = ctx->d_rec_orig;
   a.sup = ctx->d_sup;
+  a.sup_unit = ctx->d_sup + 3 * (size_t)ctx->prob.n_support;
   a.nsup = ctx->prob.n_support;
   a.rhs_taylor = ctx->rhs_taylor;
   a.sup_tensor3 = ctx->sup_tensor3;
@@ -38,9 +40,11 @@ int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long 
   const int e = 2 + ctx->es.nterms;
   auto rows = [&](int W) { return (a.k + W - 1) / W * W + (e + W - 1) / W * W; };
   cudaError_t err;
-  static const bool no_small = getenv("GSK_NO_SMALL_KERNEL") != nullptr;  // development switch
+  static const bool no_small = GSK_DEV_ENV("GSK_NO_SMALL_KERNEL") != nullptr;  // development switch
+  static const int wpt_min_k = GSK_DEV_ENV("GSK_WPT_MIN_K") ? atoi(GSK_DEV_ENV("GSK_WPT_MIN_K")) : 32;  // development switch
   if (!no_small && a.k <= gsk_local::SK_KMAX && (ctx->es.kind == GSK_EST_SIMPLE || ctx->es.nterms == 1))
     err = gsk_local_launch_small(a, st);
+  else if (a.k > wpt_min_k && a.k <= 64 && e <= 8) err = gsk_local_launch_wpt(a, e, st);  // block-pool kernel (C5: k = 64)
   else if (rows(4) <= 12) err = gsk_local_launch_A(a, e, st);
   else if (rows(4) <= 24) err = gsk_local_launch_B(a, e, st);
   else if (rows(8) <= 40) err = gsk_local_launch_C(a, e, st);

@@ -447,7 +447,7 @@ int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long 
     // staging capacity: just enough for the block a tile is expected to scan (smaller shared-memory footprint
     // → more resident CTAs, which is what the latency-bound insertion loop needs); larger blocks are simply
     // processed in several chunks. GSK_SCAP overrides (development tunable).
-    static const int scap_env = getenv("GSK_SCAP") ? atoi(getenv("GSK_SCAP")) : 0;
+    static const int scap_env = GSK_DEV_ENV("GSK_SCAP") ? atoi(GSK_DEV_ENV("GSK_SCAP")) : 0;
     double expect = 512.0;
     const int dim = ctx->tg.dim;
     if (ctx->tg.is_grid && ctx->bins.ncells > 0) {
@@ -494,7 +494,7 @@ int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long 
     nblocks = (unsigned)((count + NT - 1) / NT);
   }
   cudaError_t e;
-  static const int heap_min_k = getenv("GSK_HEAP_MIN_K") ? atoi(getenv("GSK_HEAP_MIN_K")) : 24;  // development tunable
+  static const int heap_min_k = GSK_DEV_ENV("GSK_HEAP_MIN_K") ? atoi(GSK_DEV_ENV("GSK_HEAP_MIN_K")) : 24;  // development tunable
   const bool heap = a.k >= heap_min_k;
 #define GSK_LAUNCH_SEARCH(TX, TY, TZ, D, H)                                                                        \
   do {                                                                                                             \

@@ -6,6 +6,7 @@ mirrored here in Python with the reference's names, argument meaning and error b
 julia/GSKrige.jl is the same logic as a Julia shim over the same C ABI.
 
 Mirrors (reference file:line):
+  IDWSolver / LWRSolver .............. src/estimation/idw.jl:50-148 / src/estimation/lwr.jl:53-152
   KrigingSolver + parameters ........ src/estimation/krig.jl:64-74
   preprocess ......................... src/estimation/krig.jl:76-128
   solve .............................. src/estimation/krig.jl:130-164
@@ -209,15 +210,55 @@ class Euclidean:
 
 
 class LinearPath:
-    pass
+    """Meshes' LinearPath: the domain's own order, 1:nelements."""
 
 
 class MultiGridPath:
-    pass
+    """Meshes' MultiGridPath: coarse-to-fine traversal of a grid [3P-RECALLED, V10: restated as — for step sizes
+    Δ = 2^L, 2^(L−1), …, 1 with 2^L >= the largest grid dimension, visit in column-major order every not yet visited
+    cell whose (0-based) indices are all multiples of Δ]. The C ABI takes the order as an explicit array, so the Julia
+    shim passes Meshes' own `traverse` result and does not depend on this restatement."""
 
 
 class RandomPath:
-    pass
+    """Meshes' RandomPath: a random permutation (the reference draws it from Julia's RNG; here numpy's, seedable)."""
+
+    def __init__(self, seed=None):
+        self.seed = seed
+
+
+def traverse(domain, path):
+    """ref call sites src/estimation/krig.jl:179,204 — the visiting order as 0-based linear indices, or None for the
+    domain's own order (LinearPath)."""
+    if path is None or isinstance(path, LinearPath):
+        return None
+    n = domain.nelements()
+    if isinstance(path, RandomPath):
+        return np.random.default_rng(path.seed).permutation(n).astype(np.int64)
+    if isinstance(path, MultiGridPath):
+        if not isinstance(domain, CartesianGrid):
+            raise _unsupported("MultiGridPath over a domain that is not a CartesianGrid")
+        dims = domain.dims
+        lin = np.arange(n, dtype=np.int64)
+        idx, rem = [], lin
+        for d in dims:
+            idx.append(rem % d)
+            rem = rem // d
+        level = np.zeros(n, dtype=np.int64)          # the largest power of two dividing every index of the cell
+        top = max(1, int(math.ceil(math.log2(max(dims)))) if max(dims) > 1 else 1)
+        done = np.zeros(n, dtype=bool)
+        order = []
+        for lv in range(top, -1, -1):
+            step = 1 << lv
+            sel = np.ones(n, dtype=bool)
+            for i in idx:
+                sel &= (i % step) == 0
+            sel &= ~done
+            order.append(lin[sel])
+            done |= sel
+        del level
+        return np.concatenate(order).astype(np.int64)
+    raise _unsupported(f"path {type(path).__name__}")
 
 
 # --------------------------------------------------------------------------------------
@@ -469,7 +510,7 @@ def preprocess(problem: EstimationProblem, solver: KrigingSolver) -> dict:
     return preproc
 
 
-def _problem_spec(problem_samples: GeoTable, pdomain, var, pp, *, local: bool) -> _abi.ProblemSpec:
+def _problem_spec(problem_samples: GeoTable, pdomain, var, pp, *, local: bool, order=None) -> _abi.ProblemSpec:
     est = pp["estimator"]
     searcher = pp["searcher"]
     gamma = est.variogram
@@ -484,7 +525,8 @@ def _problem_spec(problem_samples: GeoTable, pdomain, var, pp, *, local: bool) -
     if embeddim(pdomain) != dim:
         raise ValueError("sample and target domains have different embedding dimensions")
     kw = dict(coords=[sdom.coords[d] for d in range(dim)], values=problem_samples.table[var],
-              vario_kind=gamma.kind, vario_range=gamma.range, vario_sill=gamma.sill, vario_nugget=gamma.nugget)
+              vario_kind=gamma.kind, vario_range=gamma.range, vario_sill=gamma.sill, vario_nugget=gamma.nugget,
+              target_order=order)
     if isinstance(pdomain, CartesianGrid):
         kw.update(grid_dims=pdomain.dims, grid_origin=pdomain.origin, grid_spacing=pdomain.spacing,
                   support=_abi.default_support(pdomain.spacing, gamma.range))
@@ -509,21 +551,31 @@ def _problem_spec(problem_samples: GeoTable, pdomain, var, pp, *, local: bool) -
     return _abi.ProblemSpec(**kw)
 
 
-def exactsolve(problem: EstimationProblem, var: str, preproc: dict, ctx: Optional[_abi.Context] = None):
+def _path_order(pdomain, path, path_order: bool):
+    """The traversal order handed to the library: the reference maps over `traverse(pdomain, path)` and returns the
+    predictions in VISITING order without permuting back (krig.jl:179-183, 204-231), so for a non-linear path row j of
+    the result belongs to the j-th visited cell. `path_order=False` asks for domain order instead."""
+    return traverse(pdomain, path) if path_order else None
+
+
+def exactsolve(problem: EstimationProblem, var: str, preproc: dict, ctx: Optional[_abi.Context] = None, path_order=True):
     """ref src/estimation/krig.jl:166-186 — fit once on all samples, predict everywhere.
     One call into libgskrige.so (global system: one FP64 factorisation, batched triangular solves)."""
     pp = preproc[var]
-    spec = _problem_spec(problem.data(), problem.domain(), var, pp, local=False)
+    spec = _problem_spec(problem.data(), problem.domain(), var, pp, local=False,
+                         order=_path_order(problem.domain(), pp["path"], path_order))
     mean, variance = (ctx or default_context()).krige(spec)
     return mean, variance
 
 
-def approxsolve(problem: EstimationProblem, var: str, preproc: dict, ctx: Optional[_abi.Context] = None):
+def approxsolve(problem: EstimationProblem, var: str, preproc: dict, ctx: Optional[_abi.Context] = None, path_order=True):
     """ref src/estimation/krig.jl:188-234 — per-location search → fit → predict, as ONE library call.
-    Locations with fewer than `minneighbors` neighbours come back masked (the reference's `missing`)."""
+    Locations with fewer than `minneighbors` neighbours come back masked (the reference's `missing`). Only the
+    neighbour COUNTS (4 B per target) come back with the two fields, never the index lists."""
     pp = preproc[var]
-    spec = _problem_spec(problem.data(), problem.domain(), var, pp, local=True)
-    mean, variance, nneigh, _ = (ctx or default_context()).krige(spec, want_neighbors=True)
+    spec = _problem_spec(problem.data(), problem.domain(), var, pp, local=True,
+                         order=_path_order(problem.domain(), pp["path"], path_order))
+    mean, variance, nneigh = (ctx or default_context()).krige(spec, want_nneigh=True)
     miss = nneigh < max(int(pp["minneighbors"]), 1)
     if miss.any():
         mean = np.ma.MaskedArray(mean, mask=miss)
@@ -531,12 +583,7 @@ def approxsolve(problem: EstimationProblem, var: str, preproc: dict, ctx: Option
     return mean, variance
 
 
-def solve(problem: EstimationProblem, solver: KrigingSolver, ctx: Optional[_abi.Context] = None) -> GeoTable:
-    """ref src/estimation/krig.jl:130-164. Result columns: `var` and `var_variance` (units: u and u²).
-
-    Results are in domain (linear-index) order for every `path`: Kriging predictions do not depend
-    on the visiting order, so paths need no device support (the reference returns them in path
-    order without permuting back, krig.jl:179-183 — see DESIGN.md 'Deviations')."""
+def _solve_kriging(problem: EstimationProblem, solver: KrigingSolver, ctx, path_order) -> GeoTable:
     pdomain = problem.domain()
     preproc = preprocess(problem, solver)
     mus, sigmas = {}, {}
@@ -544,12 +591,127 @@ def solve(problem: EstimationProblem, solver: KrigingSolver, ctx: Optional[_abi.
         pp = preproc[var]
         prob = EstimationProblem(pp["samples"], pdomain, var)            # krig.jl:148
         if pp["maxneighbors"] is None:                                  # krig.jl:151
-            varmu, varsigma = exactsolve(prob, var, preproc, ctx)
+            varmu, varsigma = exactsolve(prob, var, preproc, ctx, path_order)
         else:
-            varmu, varsigma = approxsolve(prob, var, preproc, ctx)
+            varmu, varsigma = approxsolve(prob, var, preproc, ctx, path_order)
         unit = pp["unit"]
         if unit is not NoUnits:
             varmu, varsigma = Quantities(varmu, unit), Quantities(varsigma, unit ** 2)  # krig.jl:160
         mus[var] = varmu
         sigmas[f"{var}_variance"] = varsigma
     return georef({**mus, **sigmas}, pdomain)                           # krig.jl:163
+
+
+# --------------------------------------------------------------------------------------
+# IDWSolver / LWRSolver: same searcher, traversal and centroid step, other per-location body
+# --------------------------------------------------------------------------------------
+_IDW_DEFAULTS = dict(minneighbors=1, maxneighbors=None, neighborhood=None, distance=None, exponent=1, path=None)
+_LWR_DEFAULTS = dict(minneighbors=1, maxneighbors=None, neighborhood=None, distance=None, weightfun=None, path=None)
+
+
+class _SimpleSolver:
+    _defaults: dict = {}
+
+    def __init__(self, *pairs, **kwpairs):
+        self.vparams = {}
+        for item in list(pairs) + list(kwpairs.items()):
+            for var, params in (list(item.items()) if isinstance(item, dict) else [item]):
+                unknown = set(params) - set(self._defaults)
+                if unknown:
+                    raise TypeError(f"unknown {type(self).__name__} parameter(s) {sorted(unknown)} for variable {var}")
+                self.vparams[var] = dict(params)
+
+    def params(self, var):
+        p = dict(self._defaults)
+        p.update(self.vparams.get(var, {}))
+        if p["distance"] is None:
+            p["distance"] = Euclidean()
+        if p["path"] is None:
+            p["path"] = LinearPath()
+        return p
+
+
+class IDWSolver(_SimpleSolver):
+    """``IDWSolver(z=dict(maxneighbors=3))`` — parameters and defaults: ref src/estimation/idw.jl:50-57."""
+    _defaults = _IDW_DEFAULTS
+
+
+class LWRSolver(_SimpleSolver):
+    """``LWRSolver(z=dict(maxneighbors=10))`` — parameters and defaults: ref src/estimation/lwr.jl:53-60. Only the
+    default weight function h -> exp(-3 h^2) crosses the C ABI (`weightfun=None`)."""
+    _defaults = _LWR_DEFAULTS
+
+
+def _solve_simple(problem: EstimationProblem, solver: _SimpleSolver, ctx, path_order) -> GeoTable:
+    """ref src/estimation/idw.jl:59-148 and src/estimation/lwr.jl:62-152 (host part; the estimation loop is one library call)."""
+    pdata = problem.data()
+    ddomain = pdata.domain
+    pdomain = problem.domain()
+    if not isinstance(ddomain, PointSet):
+        raise _unsupported("sample domains that are not point sets")
+    is_idw = isinstance(solver, IDWSolver)
+    mus, sigmas = {}, {}
+    for var in problem.variables():
+        p = solver.params(var)
+        vals, missing = _split_missing(pdata.table[var].values if isinstance(pdata.table[var], Quantities) else pdata.table[var])
+        dinds = np.flatnonzero(~missing)                                   # idw.jl:78 / lwr.jl:81
+        sdom = ddomain.view(dinds)
+        n = sdom.nelements()
+        nmin = int(p["minneighbors"])
+        nmax = n if p["maxneighbors"] is None else min(int(p["maxneighbors"]), n)
+        assert n > 0, "estimation requires data"                           # idw.jl:95 / lwr.jl:97
+        if is_idw:
+            assert p["exponent"] > 0, "exponent must be positive"          # idw.jl:96
+        elif p["weightfun"] is not None:
+            raise _unsupported("a custom LWR `weightfun` (an arbitrary closure)")
+        assert nmin <= nmax, "invalid min/max number of neighbors"         # idw.jl:97 / lwr.jl:98
+        if not isinstance(p["distance"], Euclidean):
+            raise _unsupported("non-Euclidean `distance`")
+        searcher = searcher_ui(sdom, p["maxneighbors"], p["distance"], p["neighborhood"])   # idw.jl:100 / lwr.jl:101
+        z = uadjust(pdata.table[var])                                      # idw.jl:111 / lwr.jl:112
+        unit = elunit(z)
+        zvals, _ = _split_missing(z.values if isinstance(z, Quantities) else z)
+        dim = sdom.dim
+        if embeddim(pdomain) != dim:
+            raise ValueError("sample and target domains have different embedding dimensions")
+        k = 0 if p["maxneighbors"] is None else searcher.k
+        if k > _abi.GSK_MAX_NEIGHBORS:
+            raise _unsupported(f"maxneighbors > {_abi.GSK_MAX_NEIGHBORS} (omit it to use every sample)")
+        kw = dict(coords=[sdom.coords[d] for d in range(dim)], values=zvals[dinds], max_neighbors=k, min_neighbors=nmin,
+                  solver=_abi.SOLVER_IDW if is_idw else _abi.SOLVER_LWR, idw_exponent=float(p.get("exponent", 1.0)),
+                  target_order=_path_order(pdomain, p["path"], path_order))
+        if isinstance(pdomain, CartesianGrid):
+            kw.update(grid_dims=pdomain.dims, grid_origin=pdomain.origin, grid_spacing=pdomain.spacing)
+        elif isinstance(pdomain, PointSet):
+            kw.update(points=pdomain.centroids())
+        else:
+            raise _unsupported(f"target domain {type(pdomain).__name__}")
+        if k > 0 and isinstance(searcher, KBallSearch):
+            kw.update(ball_radius=searcher.ball.radius())
+        spec = _abi.ProblemSpec(**kw)
+        mu, sig, nneigh = (ctx or default_context()).krige(spec, want_nneigh=True)
+        miss = nneigh < max(nmin, 1)                                       # idw.jl:121-122 → (missing, missing)
+        if miss.any():
+            mu, sig = np.ma.MaskedArray(mu, mask=miss), np.ma.MaskedArray(sig, mask=miss)
+        if is_idw:
+            mus[var] = Quantities(mu, unit) if unit is not NoUnits else mu
+            sigmas[f"{var}_distance"] = sig                                # idw.jl:146: no unit on the distance column
+        else:
+            mus[var] = Quantities(mu, unit) if unit is not NoUnits else mu
+            sigmas[f"{var}_variance"] = Quantities(sig, unit ** 2) if unit is not NoUnits else sig   # lwr.jl:152
+    return georef({**mus, **sigmas}, pdomain)
+
+
+def solve(problem: EstimationProblem, solver, ctx: Optional[_abi.Context] = None, path_order: bool = True) -> GeoTable:
+    """ref src/estimation/krig.jl:130-164 (KrigingSolver: columns `var`, `var_variance`, units u and u²),
+    src/estimation/idw.jl:59-148 (IDWSolver: `var`, `var_distance`), src/estimation/lwr.jl:62-152 (LWRSolver: `var`,
+    `var_variance`).
+
+    Row order: for a non-linear `path` the reference returns its predictions in VISITING order (it maps over
+    `traverse(pdomain, path)` and never permutes back), and so does this function by default; `path_order=False`
+    returns domain (linear-index) order for every path — predictions do not depend on the visiting order."""
+    if isinstance(solver, KrigingSolver):
+        return _solve_kriging(problem, solver, ctx, path_order)
+    if isinstance(solver, _SimpleSolver):
+        return _solve_simple(problem, solver, ctx, path_order)
+    raise TypeError(f"solve: unsupported solver {type(solver).__name__}")

@@ -1,5 +1,6 @@
 /*
- * gsk_oracle.c — CPU restatement of GeoStatsSolvers.jl's Kriging estimation path.
+ * gsk_oracle.c — CPU restatement of GeoStatsSolvers.jl's Kriging estimation path (and of the IDW / LWR
+ * per-location bodies that share its searcher: src/estimation/idw.jl:112-142, src/estimation/lwr.jl:113-146).
  *
  * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT. Only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs may load it. libgskrige.so never links
@@ -98,6 +99,7 @@ int64_t gsk_oracle_num_targets(const gsk_problem *p) {
 
 static void target_center(const gsk_problem *p, int64_t lin, double *c) {
   c[0] = c[1] = c[2] = 0.0;
+  if (p->target_order) lin = p->target_order[lin]; /* traverse(pdomain, path): the j-th visited target (krig.jl:179,204) */
   if (p->grid_dims[0] > 0) {
     int64_t rem = lin;
     for (int d = 0; d < p->dim; d++) {
@@ -436,6 +438,99 @@ static void predict(const gsk_problem *p, const vario_t *v, const double *xyz, c
   *var_out = s2;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * IDW (ref: src/estimation/idw.jl:118-140) and LWR (ref: src/estimation/lwr.jl:119-145) bodies for one target, given
+ * the neighbours `nb` (sorted ascending by distance, as searchdists! returns them) and their squared distances.
+ * ---------------------------------------------------------------------------------------- */
+static double idw_pow(double d, double e) { /* Julia: ds .^ exponent — exact products for the small integer exponents */
+  if (e == 1.0) return d;
+  if (e == 2.0) return d * d;
+  if (e == 3.0) return d * d * d;
+  return pow(d, e);
+}
+
+static void idw_predict(const gsk_problem *p, const int32_t *nb, const double *d2, int nn, double *mu, double *sig) {
+  double sw = 0.0;
+  for (int i = 0; i < nn; i++) sw += 1.0 / idw_pow(sqrt(d2[i]), p->idw_exponent); /* ws = 1 ./ ds .^ exponent; Σw = sum(ws) */
+  if (isinf(sw)) { /* some distance is zero: j = findfirst(iszero, ds) */
+    for (int i = 0; i < nn; i++)
+      if (d2[i] == 0.0) { *mu = p->values[nb[i]]; break; }
+    *sig = 0.0;
+    return;
+  }
+  double acc = 0.0;
+  for (int i = 0; i < nn; i++) acc += ((1.0 / idw_pow(sqrt(d2[i]), p->idw_exponent)) / sw) * p->values[nb[i]];
+  *mu = acc;
+  double dmin = sqrt(d2[0]);
+  for (int i = 1; i < nn; i++) dmin = fmin(dmin, sqrt(d2[i]));
+  *sig = dmin; /* σ = minimum(ds) */
+}
+
+/* m×m (m <= 4) LU with partial pivoting, two right-hand sides — Julia's `A \ b` for a square matrix */
+static int lu_solve2(int m, double A[4][4], double *b, double *b2) {
+  for (int c = 0; c < m; c++) {
+    int piv = c;
+    double best = fabs(A[c][c]);
+    for (int r = c + 1; r < m; r++)
+      if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); piv = r; }
+    if (!(best > 0.0)) return 0;
+    if (piv != c) {
+      for (int j = 0; j < m; j++) { double t = A[c][j]; A[c][j] = A[piv][j]; A[piv][j] = t; }
+      double t = b[c]; b[c] = b[piv]; b[piv] = t;
+      t = b2[c]; b2[c] = b2[piv]; b2[piv] = t;
+    }
+    for (int r = c + 1; r < m; r++) {
+      double f = A[r][c] / A[c][c];
+      for (int j = c + 1; j < m; j++) A[r][j] -= f * A[c][j];
+      b[r] -= f * b[c];
+      b2[r] -= f * b2[c];
+    }
+  }
+  for (int r = m - 1; r >= 0; r--) {
+    double s = b[r], s2 = b2[r];
+    for (int j = r + 1; j < m; j++) { s -= A[r][j] * b[j]; s2 -= A[r][j] * b2[j]; }
+    b[r] = s / A[r][r];
+    b2[r] = s2 / A[r][r];
+  }
+  return 1;
+}
+
+static void lwr_predict(const gsk_problem *p, const double *xyz, const int32_t *nb, const double *d2, int nn,
+                        const double *ctr, double *mu, double *sig) {
+  int dim = p->dim, m = dim + 1;
+  double dmax = 0.0;
+  for (int i = 0; i < nn; i++) dmax = fmax(dmax, sqrt(d2[i])); /* δs = ds ./ maximum(ds) */
+  double A[4][4] = {{0}}, bz[4] = {0, 0, 0, 0}, x0[4] = {1.0, ctr[0], ctr[1], ctr[2]};
+  for (int i = 0; i < nn; i++) {
+    double h = sqrt(d2[i]) / dmax;
+    double w = exp(-3.0 * (h * h)); /* weightfun default, lwr.jl:58 */
+    const double *q = xyz + 3 * (int64_t)nb[i];
+    double x[4] = {1.0, q[0], q[1], q[2]};
+    for (int a = 0; a < m; a++) {
+      double wx = x[a] * w;
+      for (int b = 0; b < m; b++) A[a][b] += wx * x[b]; /* Xₗ' Wₗ Xₗ */
+      bz[a] += wx * p->values[nb[i]];                   /* Xₗ' Wₗ zₗ */
+    }
+  }
+  if (!lu_solve2(m, A, bz, x0)) { *mu = NAN; *sig = NAN; return; } /* the reference throws SingularException */
+  double c0[4] = {1.0, ctr[0], ctr[1], ctr[2]};
+  double zhat = 0.0;
+  for (int a = 0; a < m; a++) zhat += bz[a] * c0[a]; /* ẑₒ = θₗ ⋅ xₒ */
+  double rr = 0.0;
+  for (int i = 0; i < nn; i++) {
+    double h = sqrt(d2[i]) / dmax;
+    double w = exp(-3.0 * (h * h));
+    const double *q = xyz + 3 * (int64_t)nb[i];
+    double x[4] = {1.0, q[0], q[1], q[2]};
+    double xu = 0.0;
+    for (int a = 0; a < m; a++) xu += x[a] * x0[a];
+    double ri = w * xu; /* rₗ = Wₗ Xₗ (Xₗ'WₗXₗ \ xₒ) */
+    rr += ri * ri;
+  }
+  *mu = zhat;
+  *sig = sqrt(rr); /* r̂ₒ = norm(rₗ) */
+}
+
 /* the searcher of the last local call (see gsk_oracle_krige) */
 static struct { double *xyz; kdtree_t *tree; int64_t n; int dim; uint64_t key; } g_prep;
 
@@ -499,6 +594,29 @@ int gsk_oracle_krige(const gsk_problem *p, double *mean_out, double *var_out, in
 #endif
   (void)nt_call;
 
+  if (p->solver != GSK_SOLVER_KRIGING && p->max_neighbors == 0) {
+    /* ---- IDW / LWR with every sample as a neighbour (maxneighbors === nothing: nmax = n, idw.jl:93, lwr.jl:95) ---- */
+#pragma omp parallel num_threads(nt_call)
+    {
+      cand_t *best = (cand_t *)malloc(sizeof(cand_t) * (size_t)n);
+      int32_t *nb = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+      double *dd = (double *)malloc(sizeof(double) * (size_t)n);
+#pragma omp for schedule(dynamic, 16)
+      for (int64_t t = 0; t < count; t++) {
+        double ctr[3];
+        target_center(p, first + t, ctr);
+        int cnt = knn_brute(p, xyz, ctr, (int)n, best);
+        for (int i = 0; i < cnt; i++) { nb[i] = best[i].idx; dd[i] = best[i].d2; }
+        if (nneigh_out) nneigh_out[t] = cnt;
+        if (cnt < p->min_neighbors || cnt == 0) { mean_out[t] = NAN; var_out[t] = NAN; continue; }
+        if (p->solver == GSK_SOLVER_IDW) idw_predict(p, nb, dd, cnt, &mean_out[t], &var_out[t]);
+        else lwr_predict(p, xyz, nb, dd, cnt, ctr, &mean_out[t], &var_out[t]);
+      }
+      free(best); free(nb); free(dd);
+    }
+    free(xyz);
+    return GSK_OK;
+  }
   if (p->max_neighbors == 0) {
     /* ---- exactsolve: fit once on all samples, predict everywhere (krig.jl:176-180) ---- */
     int m = (int)n + c;
@@ -548,6 +666,7 @@ int gsk_oracle_krige(const gsk_problem *p, double *mean_out, double *var_out, in
     f.piv = (int32_t *)malloc(sizeof(int32_t) * (size_t)mmax);
     double *rhs = (double *)malloc(sizeof(double) * (size_t)mmax);
     double *sol = (double *)malloc(sizeof(double) * (size_t)mmax);
+    double *dd = (double *)malloc(sizeof(double) * (size_t)k);
 #pragma omp for schedule(dynamic, 64)
     for (int64_t t = 0; t < count; t++) {
       double ctr[3];
@@ -569,10 +688,16 @@ int gsk_oracle_krige(const gsk_problem *p, double *mean_out, double *var_out, in
         var_out[t] = NAN;
         continue;
       }
+      if (p->solver != GSK_SOLVER_KRIGING) { /* idw.jl:118-140 / lwr.jl:119-145 on the same neighbour list */
+        for (int i = 0; i < nn; i++) dd[i] = best[i].d2;
+        if (p->solver == GSK_SOLVER_IDW) idw_predict(p, nb, dd, nn, &mean_out[t], &var_out[t]);
+        else lwr_predict(p, xyz, nb, dd, nn, ctr, &mean_out[t], &var_out[t]);
+        continue;
+      }
       fit_system(p, &v, xyz, nb, nn, c, exps, &f);
       predict(p, &v, xyz, nb, &f, exps, ctr, rhs, sol, &mean_out[t], &var_out[t]);
     }
-    free(best); free(nb); free(f.A); free(f.piv); free(rhs); free(sol);
+    free(best); free(nb); free(f.A); free(f.piv); free(rhs); free(sol); free(dd);
   }
   if (!tree) free(xyz); /* brute-force search: nothing is kept; otherwise g_prep owns xyz and the tree */
   return GSK_OK;
