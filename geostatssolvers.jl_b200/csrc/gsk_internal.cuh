@@ -83,6 +83,8 @@ struct GskLocalArgs {
   const double4 *rec_orig;  // samples in original order: {x, y, z, value}
   const double *sup;        // support offsets [3][nsup] (device)
   const double *sup_unit;   // the same in units of the variogram range
+  int sup_smem;             // set by the launcher: the kernel stages the offsets in shared memory (else it reads them from
+                            // global memory: supports above GSK_MAX_SUPPORT points, or no shared memory left for them)
   int nsup;
   double rhs_inr_lim2;      // spherical model: (1 − max|δ|/range)² (a bit less), or −1: a neighbour whose squared centroid distance in range units is below it has all its support points inside the range
   int sup_tensor3;          // the support is a tensor grid with 3 offsets per axis (the default for cells no larger than the range), x fastest

@@ -146,6 +146,14 @@ __device__ __forceinline__ void gsk_dmma16816(double (&d)[4], const double (&a)[
         "d"(b[2]), "d"(b[3]));
 }
 
+// D(8×8) += A(8×4, row) · B(4×8, col): the native FP64 tensor instruction (SASS DMMA.8x8x4; m16n8k16 is eight of
+// them). Fragments, g = lane/4, t = lane%4: a = A[g][t], b = B[t][g], d = {D[g][2t], D[g][2t+1]}.
+__device__ __forceinline__ void gsk_dmma884(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d[0]), "+d"(d[1])
+               : "d"(a), "d"(b));
+}
+
 // Sign/magnitude tests on the high word run on the integer pipe instead of the FP64 pipe (DSETP), which is the
 // pipe the kernels saturate. Valid for finite d >= 0; a subnormal d (distance below 1.5e-154) counts as zero —
 // rsqrt.approx.ftz flushes it to zero anyway.
@@ -377,7 +385,7 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sm = reinterpret_cast<double *>(smem_raw);
   double *sup = sm;  // [3][nsup]
-  const int nsup_pad = (3 * a.nsup + 3) & ~3;
+  const int nsup_pad = a.sup_smem ? ((3 * a.nsup + 3) & ~3) : 0;
   int *ctab = reinterpret_cast<int *>(sm + nsup_pad);  // element (row i, column c) of a packed factor sits at ctab[c] + i
   double *groups = sm + nsup_pad + CTAB;
 
@@ -407,7 +415,8 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
   }
 
   const double cscale = UNITG ? a.vg.inv_r : 1.0;
-  for (int i = tid; i < 3 * a.nsup; i += CTA_THREADS) sup[i] = UNITG ? a.sup[i] * cscale : a.sup[i];
+  if (a.sup_smem)
+    for (int i = tid; i < 3 * a.nsup; i += CTA_THREADS) sup[i] = UNITG ? a.sup[i] * cscale : a.sup[i];
   if (PAIRFILL)
     for (int c = tid; c < KCMAX; c += CTA_THREADS) ctab[c] = col_off<LD, A>(c) - (c & ~(A - 1));
   __syncthreads();
@@ -486,8 +495,10 @@ __global__ void __launch_bounds__(NT) local_solve_kernel(const GskLocalArgs a, c
 #pragma unroll
           for (int i = 0; i < 3; ++i) axs[d][i] = UNITG ? a.sup_ax[d][i] * cscale : a.sup_ax[d][i];
         rhs_tensor3<VK, DIM, JM, UNITG>(a, vg, axs, tcz, cx, cy, cz, bacc);
-      } else {
+      } else if (a.sup_smem) {
         rhs_block_support<VK, DIM, JM, UNITG>(a, vg, sup, tcz, cx, cy, cz, bacc);
+      } else {  // large support (or no shared memory left): every lane reads the same offset from global memory
+        rhs_block_support<VK, DIM, JM, UNITG>(a, vg, UNITG ? a.sup_unit : a.sup, tcz, cx, cy, cz, bacc);
       }
     }
     const double inv_q = 1.0 / (double)a.nsup;
@@ -897,16 +908,21 @@ inline cudaError_t launch_one(const GskLocalArgs &a, int e, cudaStream_t st) {
   constexpr int TPW = 32 / G;
   constexpr int TPC = TPW * (CTA_THREADS / 32);
   Layout L = make_layout<G, R, W, RS, DIM>(a.k, e);
-  int nsup_pad = (3 * a.nsup + 3) & ~3;
   constexpr int KCMAX = RS - W;
   constexpr int CTAB = (G == 32) ? ((KCMAX + 1) / 2 + 3) / 4 * 4 : 0;  // column-base table of the pair fill (kernel: ctab)
+  GskLocalArgs b = a;
+  // the support offsets are staged in shared memory when they are few and there is room; otherwise the kernel
+  // reads them from global memory (uniform addresses). The factor storage itself must fit.
+  int nsup_pad = (3 * a.nsup + 3) & ~3;
   size_t smem = sizeof(double) * ((size_t)nsup_pad + CTAB + (size_t)TPC * L.gsz);
+  b.sup_smem = (a.nsup <= GSK_MAX_SUPPORT && smem <= GSK_SMEM_OPTIN_MAX) ? 1 : 0;
+  if (!b.sup_smem) smem = sizeof(double) * ((size_t)CTAB + (size_t)TPC * L.gsz);
   if (smem > GSK_SMEM_OPTIN_MAX) return cudaErrorInvalidConfiguration;  // reported as GSK_ERR_UNSUPPORTED by the caller
   auto kern = local_solve_kernel<G, R, W, RS, NT, DIM, VK>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   unsigned grid = (unsigned)((a.count + TPC - 1) / TPC);
-  kern<<<grid, CTA_THREADS, smem, st>>>(a, L);
+  kern<<<grid, CTA_THREADS, smem, st>>>(b, L);
   return cudaGetLastError();
 }
 

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *sm = reinterpret_cast<double *>(smem_raw);
   double *sup = sm;
-  const int nsup_pad = (3 * a.nsup + 3) & ~3;
+  const int nsup_pad = a.sup_smem ? ((3 * a.nsup + 3) & ~3) : 0;
   const int tid = threadIdx.x, lane = tid & 31, l = lane & 3, grp = tid >> 2, gbase = lane & ~3;
   const long long t = (long long)blockIdx.x * TPC + grp;
   const bool live = t < a.count;
@@ -53,8 +53,10 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const
   // evaluation; no drift terms here that would need the coordinates themselves)
   constexpr bool UNIT = (VK == GSK_VARIO_SPHERICAL);
   const double cscale = UNIT ? a.vg.inv_r : 1.0;
-  for (int i = tid; i < 3 * a.nsup; i += NTH) sup[i] = UNIT ? a.sup[i] * cscale : a.sup[i];
+  if (a.sup_smem)
+    for (int i = tid; i < 3 * a.nsup; i += NTH) sup[i] = UNIT ? a.sup[i] * cscale : a.sup[i];
   __syncthreads();
+
   double *S = sm + nsup_pad + (size_t)grp * SK_GSZ;
   double *Sl = S + l;
   const GskVario vg = a.vg;
@@ -121,7 +123,10 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const
   }
   // ---- phase 2: block-support RHS, q outermost (5 independent chains per lane) ----
   if (UNIT) tc[0] = tc[1] = tc[2] = 0.0;  // the centroid is the local origin
-  if (VK == GSK_VARIO_SPHERICAL) {
+  if (!a.sup_smem) {
+    // supports above GSK_MAX_SUPPORT points: read from global memory (uniform addresses), in the same frame
+    rhs_block_support<VK, DIM, R, UNIT, NUG0>(a, vg, UNIT ? a.sup_unit : a.sup, tc, nx, ny, nz, bacc);
+  } else if (VK == GSK_VARIO_SPHERICAL) {
     // warp-uniform fast path: every support point of every neighbour of the warp's targets lies inside the range
     // (the coordinates are centroid-relative in range units here), so the range select is not needed
     bool inr = true;
@@ -286,13 +291,15 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const
 template <int DIM, int VK, bool FULL, bool NUG0 = false, int NTH = 256>
 inline cudaError_t launch_small_full(const GskLocalArgs &a, cudaStream_t st) {
   const int KC = (a.k + 3) / 4 * 4;
-  const int nsup_pad = (3 * a.nsup + 3) & ~3;
+  GskLocalArgs b = a;
+  b.sup_smem = (a.nsup <= GSK_MAX_SUPPORT) ? 1 : 0;
+  const int nsup_pad = b.sup_smem ? ((3 * a.nsup + 3) & ~3) : 0;
   const size_t smem = sizeof(double) * ((size_t)nsup_pad + (NTH / 4) * (size_t)SK_GSZ);
   auto kern = local_solve_small_kernel<DIM, VK, FULL, NUG0, NTH>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;
   const unsigned grid = (unsigned)((a.count + NTH / 4 - 1) / (NTH / 4));
-  kern<<<grid, NTH, smem, st>>>(a, KC);
+  kern<<<grid, NTH, smem, st>>>(b, KC);
   return cudaGetLastError();
 }
 

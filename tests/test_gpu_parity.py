@@ -41,8 +41,7 @@ def test_reference_testset_through_solve(gsk, ctx):
     grid2d = gsk.CartesianGrid((100, 100), (0.5, 0.5), (1.0, 1.0))
     prob2d = gsk.EstimationProblem(data2d, grid2d, "z")
     for params in (dict(variogram=g35), dict(variogram=g35, maxneighbors=3),
-                   dict(variogram=g35, maxneighbors=3, neighborhood=gsk.MetricBall(100.0)),
-                   dict(variogram=g35, maxneighbors=3, neighborhood=gsk.MetricBall(100.0), path=gsk.MultiGridPath())):
+                   dict(variogram=g35, maxneighbors=3, neighborhood=gsk.MetricBall(100.0))):
         sol = gsk.solve(prob2d, gsk.KrigingSolver(z=params), ctx=ctx)
         Z = gsk.asarray(sol, "z")
         S = np.asarray(sol.z)
@@ -50,6 +49,23 @@ def test_reference_testset_through_solve(gsk, ctx):
             i, j = int(i), int(j)
             assert abs(Z[i - 1, j - 1] - expected) < 1e-3                          # krig.jl:35-37,50-52
             assert abs(S[(i - 1) + (j - 1) * 100] - expected) < 1e-3               # krig.jl:70-72 (LinearIndices)
+    # custom path (krig.jl:78-90; the reference only checks that it runs): the reference maps over
+    # traverse(grid, MultiGridPath()) and returns the predictions in VISITING order (krig.jl:204-231) — so must we;
+    # `path_order=False` gives the same field in domain order
+    base = dict(variogram=g35, maxneighbors=3, neighborhood=gsk.MetricBall(100.0))
+    lin = gsk.solve(prob2d, gsk.KrigingSolver(z=base), ctx=ctx)
+    for path in (gsk.MultiGridPath(), gsk.RandomPath(seed=2021)):
+        order = gsk.traverse(grid2d, path)
+        assert sorted(order.tolist()) == list(range(grid2d.nelements()))
+        sol = gsk.solve(prob2d, gsk.KrigingSolver(z=dict(base, path=path)), ctx=ctx)
+        assert np.array_equal(np.asarray(sol.z), np.asarray(lin.z)[order])
+        assert np.array_equal(np.asarray(sol["z_variance"]), np.asarray(lin["z_variance"])[order])
+        dom = gsk.solve(prob2d, gsk.KrigingSolver(z=dict(base, path=path)), ctx=ctx, path_order=False)
+        assert np.array_equal(np.asarray(dom.z), np.asarray(lin.z))
+    glob_lin = gsk.solve(prob2d, gsk.KrigingSolver(z=dict(variogram=g35)), ctx=ctx)
+    glob_mg = gsk.solve(prob2d, gsk.KrigingSolver(z=dict(variogram=g35, path=gsk.MultiGridPath())), ctx=ctx)
+    order = gsk.traverse(grid2d, gsk.MultiGridPath())
+    np.testing.assert_allclose(np.asarray(glob_mg.z), np.asarray(glob_lin.z)[order], rtol=0, atol=1e-12)
 
 
 @pytest.mark.parametrize("k,radius", [(0, None), (3, None), (3, 100.0)])

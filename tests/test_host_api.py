@@ -180,7 +180,7 @@ def test_julia_shim_struct_matches_the_header(gsk):
         decl = " ".join(decl.split())
         if not decl:
             continue
-        m = re.match(r"(const double \*|double|int32_t|int64_t|uint32_t)\s*(.*)", decl)
+        m = re.match(r"(const double \*|const int64_t \*|double|int32_t|int64_t|uint32_t)\s*(.*)", decl)
         assert m, decl
         ctype = m.group(1).strip()
         for name in m.group(2).split(","):
@@ -189,7 +189,8 @@ def test_julia_shim_struct_matches_the_header(gsk):
             c_fields.append((arr.group(1), ctype, 3) if arr else (name, ctype, 1))
     jl = (root / "julia" / "GSKrige.jl").read_text()
     jbody = re.search(r"struct GskProblem\n(.*?)\nend", jl, re.S).group(1)
-    width = {"Int32": "int32_t", "Int64": "int64_t", "UInt32": "uint32_t", "Float64": "double", "Ptr{Float64}": "const double *"}
+    width = {"Int32": "int32_t", "Int64": "int64_t", "UInt32": "uint32_t", "Float64": "double", "Ptr{Float64}": "const double *",
+             "Ptr{Int64}": "const int64_t *"}
     j_fields = []
     for line in jbody.splitlines():
         name, typ = [t.strip() for t in line.split("::")]
