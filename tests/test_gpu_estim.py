@@ -71,7 +71,7 @@ def test_idw_lwr_through_solve_units_and_reference_problems(gsk, ctx):
     z = np.asarray(sol.z)
     assert z.shape == (10000,) and np.all((z >= 0.0) & (z <= 1.0)) and "z_distance" in sol.names()
     Z = gsk.asarray(sol, "z")
-    assert abs(Z[24, 24] - 1.0) < 2e-2 and abs(Z[49, 74] - 0.0) < 2e-2 and abs(Z[74, 49] - 1.0) < 2e-2   # cf. idw.jl:71-73
+    assert abs(Z[24, 24] - 1.0) < 5e-2 and abs(Z[49, 74] - 0.0) < 5e-2 and abs(Z[74, 49] - 1.0) < 5e-2   # cf. idw.jl:71-73
     order = gsk.traverse(grid, gsk.MultiGridPath())
     solp = gsk.solve(prob, gsk.IDWSolver(z=dict(maxneighbors=3, path=gsk.MultiGridPath())), ctx=ctx)
     assert np.array_equal(np.asarray(solp.z), z[order])

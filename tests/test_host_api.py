@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(gsk):
     assert sorted(set(declared)) == sorted(gsk.EXPORTED_SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.gsk_abi_version() == 1
+    assert lib.gsk_abi_version() == 2
 
 
 def test_struct_layout_matches_c(gsk, tmp_path):
@@ -78,14 +78,15 @@ class _FakeCtx:
     def __init__(self):
         self.specs = []
 
-    def krige(self, spec, want_neighbors=False):
+    def krige(self, spec, want_neighbors=False, want_nneigh=False):
         self.specs.append(spec)
+        self.asked_lists = want_neighbors
         _, count = spec.slab
         mean, var = np.zeros(count), np.ones(count)
-        if want_neighbors:
-            nn = np.full(count, spec.params["max_neighbors"], dtype=np.int32)
+        if want_neighbors or want_nneigh:
+            nn = np.full(count, spec.params["max_neighbors"] or spec.n_samples, dtype=np.int32)
             nn[:2] = 0
-            return mean, var, nn, None
+            return (mean, var, nn, None) if want_neighbors else (mean, var, nn)
         return mean, var
 
 
@@ -109,6 +110,47 @@ def test_host_mirror_solve_flow(gsk):
     assert sol.z.unit == gsk.K and repr(sol["z_variance"].unit) == "K^2"
     assert np.ma.getmaskarray(sol.z.values)[:2].all() and not np.ma.getmaskarray(sol.z.values)[2:].any()
     assert gsk.asarray(sol, "z").shape == (10, 10)
+    assert fake.asked_lists is False                             # only the neighbour COUNTS cross back, never the lists
+    # a non-linear path: the visiting order crosses the ABI (the reference returns its results in that order)
+    fake = _FakeCtx()
+    gsk.solve(problem, gsk.KrigingSolver(z=dict(variogram=gsk.GaussianVariogram(range=35.0), maxneighbors=3,
+                                                path=gsk.MultiGridPath())), ctx=fake)
+    order = fake.specs[0].target_order
+    assert order is not None and sorted(order.tolist()) == list(range(100)) and order[0] == 0
+    assert np.array_equal(order, gsk.traverse(grid, gsk.MultiGridPath()))
+    fake = _FakeCtx()
+    gsk.solve(problem, gsk.KrigingSolver(z=dict(maxneighbors=3, path=gsk.MultiGridPath())), ctx=fake, path_order=False)
+    assert fake.specs[0].target_order is None
+
+
+def test_host_mirror_idw_lwr(gsk):
+    """idw.jl:59-148 / lwr.jl:62-152: parameters, neighbour clamp, unit handling, column names."""
+    table = {"T": gsk.Quantities([-272.15, None, -273.15, -272.15], gsk.degC)}
+    data = gsk.georef(table, [(25.0, 25.0), (1.0, 1.0), (50.0, 75.0), (75.0, 50.0)])
+    grid = gsk.CartesianGrid(5, 5)
+    problem = gsk.EstimationProblem(data, grid, "T")
+    fake = _FakeCtx()
+    sol = gsk.solve(problem, gsk.IDWSolver(), ctx=fake)             # idw.jl:36-41: maxneighbors === nothing → every sample
+    spec = fake.specs[0]
+    assert spec.params["solver"] == gsk.SOLVER_IDW and spec.params["max_neighbors"] == 0 and spec.params["idw_exponent"] == 1.0
+    assert spec.n_samples == 3
+    np.testing.assert_allclose(spec.values, [1.0, 0.0, 1.0], atol=1e-12)   # °C → K
+    assert sol.names() == ["T", "T_distance"] and gsk.elunit(sol["T"]) == gsk.K and gsk.elunit(sol["T_distance"]) == gsk.NoUnits
+    fake = _FakeCtx()
+    sol = gsk.solve(problem, gsk.LWRSolver(T=dict(maxneighbors=2, neighborhood=gsk.MetricBall(30.0))), ctx=fake)
+    spec = fake.specs[0]
+    assert spec.params["solver"] == gsk.SOLVER_LWR and spec.params["max_neighbors"] == 2 and spec.params["ball_radius"] == 30.0
+    assert sol.names() == ["T", "T_variance"] and repr(gsk.elunit(sol["T_variance"])) == "K^2"
+    with pytest.raises(AssertionError, match="exponent must be positive"):        # idw.jl:96
+        gsk.solve(problem, gsk.IDWSolver(T=dict(exponent=0)), ctx=_FakeCtx())
+    with pytest.raises(AssertionError, match="invalid min/max number of neighbors"):   # idw.jl:97
+        gsk.solve(problem, gsk.IDWSolver(T=dict(minneighbors=3, maxneighbors=2)), ctx=_FakeCtx())
+    with pytest.warns(UserWarning, match="Adjusting to 3"):
+        f = _FakeCtx()
+        gsk.solve(problem, gsk.LWRSolver(T=dict(maxneighbors=9)), ctx=f)
+    assert f.specs[0].params["max_neighbors"] == 3
+    with pytest.raises(TypeError):
+        gsk.IDWSolver(T=dict(power=2))
 
 
 def test_host_mirror_global_and_estimators(gsk):
