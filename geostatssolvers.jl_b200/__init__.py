@@ -18,7 +18,8 @@ from .host import (CartesianGrid, EstimationProblem, Euclidean, ExponentialVario
                    SimpleKriging, SphericalVariogram, UniversalKriging, Unit, UnsupportedOption, approxsolve, asarray,
                    default_context, degC, elunit, embeddim, exactsolve, georef, kriging_ui, maxneighbors, nelements,
                    preprocess, searcher_ui, solve, traverse, uadjust)
-from . import sharding, synth  # noqa: F401
+from . import sharding, simulation, synth  # noqa: F401
+from .simulation import FFTGS, SimulationProblem  # noqa: F401
 from .sharding import gather_slabs, slab_bounds  # noqa: F401
 
 __version__ = "0.1.0"

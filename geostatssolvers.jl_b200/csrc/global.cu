@@ -503,9 +503,13 @@ __global__ void __launch_bounds__(256, 1) ygemm_dmma_kernel(const double *__rest
 }
 
 // ---- per-target epilogue: reduce the partials over the row tiles, then the e×e algebra ----
+struct GDual {
+  const double *dmean;  // w·b(t) per target of the batch
+  double beta[GSK_MAX_DRIFT_TERMS];
+};
 __global__ void global_epilogue_kernel(const double *__restrict__ partial, int nmt, int ne, long long nbpad,
                                        int nbatch, const double *__restrict__ GEE, GskEstimator es, GskTargets tg,
-                                       double sill, unsigned flags, long long first, GskOut out) {
+                                       double sill, unsigned flags, long long first, GskOut out, GDual dual) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nbatch) return;
   double g[2 + GSK_MAX_DRIFT_TERMS];
@@ -517,8 +521,9 @@ __global__ void global_epilogue_kernel(const double *__restrict__ partial, int n
   const double gbb = g[0], gbz = g[1];
   const int c = es.nterms;
   double mu, s2;
+  (void)gbz;  // the Gram form of the mean (Gbz − Gfz·ν) is superseded by the refined dual weights
   if (c == 0) {
-    mu = es.sk_mean + gbz;
+    mu = es.sk_mean + dual.dmean[t];
     s2 = sill - gbb;
   } else {
     double f0[GSK_MAX_DRIFT_TERMS], nu[GSK_MAX_DRIFT_TERMS], Lf[GSK_MAX_DRIFT_TERMS][GSK_MAX_DRIFT_TERMS];
@@ -560,18 +565,136 @@ __global__ void global_epilogue_kernel(const double *__restrict__ partial, int n
       for (int p = j + 1; p < c; ++p) s -= Lf[p][j] * nu[p];
       nu[j] = s / Lf[j][j];
     }
-    double mz = 0.0, mb = 0.0, mf = 0.0;
+    double mb = 0.0, mf = 0.0, mbeta = 0.0;
     for (int j = 0; j < c; ++j) {
-      mz += GEE[(1 + j) * ne + 0] * nu[j];
       mb += g[2 + j] * nu[j];
       mf += f0[j] * nu[j];
+      mbeta += dual.beta[j] * f0[j];
     }
-    mu = gbz - mz;
+    mu = dual.dmean[t] + mbeta;  // w·b(t) + β·f₀(t)
     s2 = sill - (gbb - mb + mf);
   }
   if (flags & GSK_FLAG_CLAMP_VARIANCE) s2 = (s2 > 0.0 || s2 != s2) ? s2 : 0.0;
   if (flags & GSK_FLAG_SQRT_ROUNDTRIP) { double sd = sqrt(s2); s2 = sd * sd; }
   gsk_store_result(out, t, mu, s2);
+}
+
+// ---- dual weights of the mean (plan time) -------------------------------------------------------------------
+// mean(t) = [z;0]ᵀ K⁻¹ [b(t); f₀(t)] = w·b(t) + β·f₀(t) with K [w; β] = [z; 0]: the mean needs only a dot product with the
+// right-hand side once (w, β) are known. They are obtained from the factor and then REFINED with residuals accumulated
+// in double-double arithmetic (error-free products and sums), which brings w to ~1 ulp of the solution of the assembled
+// system — the Gram form Gbz − Gfz·ν of the same mean carries ~cond(C)·eps (2e-9 on the Gaussian C1 system, round 1).
+__device__ __forceinline__ void dd_add_prod(double &hi, double &lo, double a, double b) {
+  const double p = a * b, pe = fma(a, b, -p);  // a·b = p + pe exactly
+  const double s = hi + p, bb = s - hi;
+  const double se = (hi - (s - bb)) + (p - bb);  // hi + p = s + se exactly
+  hi = s;
+  lo += se + pe;
+}
+
+// out[j] = Σ_{i>=j} X[i, j]·v[i]  (Xᵀ v, X lower triangular, column-major): one warp per column
+__global__ void xt_matvec_kernel(const double *__restrict__ X, long long ld, long long np, const double *__restrict__ v,
+                                 double *__restrict__ out) {
+  const long long j = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= np) return;
+  double s = 0.0;
+  for (long long i = j + lane; i < np; i += 32) s = fma(X[i + j * ld], v[i], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[j] = s;
+}
+
+// r[i] = z[i] − Σ_j C[i, j]·w[j] − Σ_t F[i, t]·β[t] in double-double, C re-evaluated exactly as assemble_kernel does
+template <int VK>
+__global__ void dual_residual_kernel(GArgs g, const double *__restrict__ E, int ne, const double *__restrict__ w,
+                                     GskEstimator es, const double *__restrict__ beta, double *__restrict__ r) {
+  const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= g.np) return;
+  if (i >= g.n) {  // padded rows: identity block, zero right-hand side
+    if (lane == 0) r[i] = -w[i];
+    return;
+  }
+  const double4 a = g.rec[i];
+  double hi = 0.0, lo = 0.0;
+  for (long long j = lane; j < g.n; j += 32) {
+    double c;
+    if (j == i) c = g.vg.sill;
+    else {
+      const double4 b = g.rec[j];
+      const double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+      c = gsk_cov<VK>(g.vg, fma(dz, dz, fma(dy, dy, dx * dx)));
+    }
+    dd_add_prod(hi, lo, -c, w[j]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {  // combine the lanes' double-double partial sums
+    const double oh = __shfl_xor_sync(0xffffffffu, hi, o), ol = __shfl_xor_sync(0xffffffffu, lo, o);
+    const double s = hi + oh, bb = s - hi;
+    lo += ((hi - (s - bb)) + (oh - bb)) + ol;
+    hi = s;
+  }
+  if (lane == 0) {
+    dd_add_prod(hi, lo, 1.0, E[i]);  // + z_i (E column 0 holds z − μ for Simple Kriging)
+    for (int t = 0; t < es.nterms; ++t) dd_add_prod(hi, lo, -E[i + (long long)(1 + t) * g.np], beta[t]);
+    r[i] = hi + lo;
+  }
+}
+
+// out[t] = Σ_i A[i + t·ld]·v[i] in double-double (t < nt columns of length np): one CTA per column
+__global__ void cols_dot_dd_kernel(const double *__restrict__ A, long long ld, long long np, const double *__restrict__ v,
+                                   double *__restrict__ out) {
+  __shared__ double sh[256], sl[256];
+  const double *col = A + (long long)blockIdx.x * ld;
+  double hi = 0.0, lo = 0.0;
+  for (long long i = threadIdx.x; i < np; i += 256) dd_add_prod(hi, lo, col[i], v[i]);
+  sh[threadIdx.x] = hi;
+  sl[threadIdx.x] = lo;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const double a = sh[threadIdx.x], b = sh[threadIdx.x + o];
+      const double s = a + b, bb = s - a;
+      sl[threadIdx.x] += ((a - (s - bb)) + (b - bb)) + sl[threadIdx.x + o];
+      sh[threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sh[0] + sl[0];
+}
+
+// v[i] = y[i] − Σ_t YF[i, t]·d[t]   (YF = columns 1… of Y_E)
+__global__ void sub_cols_kernel(const double *__restrict__ y, const double *__restrict__ YE, long long np, int nt,
+                                const double *__restrict__ d, double *__restrict__ v) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  double s = y[i];
+  for (int t = 0; t < nt; ++t) s = fma(-YE[i + (long long)(1 + t) * np], d[t], s);
+  v[i] = s;
+}
+
+__global__ void axpy_kernel(double *__restrict__ w, const double *__restrict__ d, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) w[i] += d[i];
+}
+
+// dmean[t] = Σ_i w[i]·B[i + t·np]: one warp per target column of the batch
+__global__ void dual_mean_kernel(const double *__restrict__ Bm, long long np, int nbatch, const double *__restrict__ w,
+                                 double *__restrict__ dmean) {
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= nbatch) return;
+  const double *col = Bm + (long long)t * np;
+  double s0 = 0.0, s1 = 0.0;
+  for (long long i = lane; i < np; i += 64) {
+    s0 = fma(col[i], w[i], s0);
+    if (i + 32 < np) s1 = fma(col[i + 32], w[i + 32], s1);
+  }
+  double s = s0 + s1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) dmean[t] = s;
 }
 
 __global__ void fill_int_kernel(int *p, long long n, int v) {
@@ -589,8 +712,98 @@ struct GlobalPlan {
   double *Dinv = nullptr;  // inverses of the diagonal blocks
   double *E = nullptr, *YE = nullptr, *GEE = nullptr;
   double *Bm = nullptr, *partial = nullptr;
+  double *w = nullptr;       // dual weights of the mean (np)
+  double *tmp = nullptr;     // 3·np + 32 scratch doubles of the refinement
+  double *dmean = nullptr;   // w·b(t) of a batch
+  double beta[GSK_MAX_DRIFT_TERMS] = {};
   long long batch = 0;
 };
+
+namespace {
+// c×c SPD solve on the host in long double (c <= 10): G x = rhs
+void host_spd_solve(int c, const double *G, int ldg, const long double *rhs, long double *x) {
+  long double A[GSK_MAX_DRIFT_TERMS][GSK_MAX_DRIFT_TERMS + 1];
+  for (int i = 0; i < c; ++i) {
+    for (int j = 0; j < c; ++j) A[i][j] = G[i * ldg + j];
+    A[i][c] = rhs[i];
+  }
+  for (int k = 0; k < c; ++k) {
+    int piv = k;
+    for (int i = k + 1; i < c; ++i)
+      if (fabsl(A[i][k]) > fabsl(A[piv][k])) piv = i;
+    for (int j = 0; j <= c; ++j) std::swap(A[k][j], A[piv][j]);
+    for (int i = k + 1; i < c; ++i) {
+      const long double f = A[i][k] / A[k][k];
+      for (int j = k; j <= c; ++j) A[i][j] -= f * A[k][j];
+    }
+  }
+  for (int i = c - 1; i >= 0; --i) {
+    long double s = A[i][c];
+    for (int j = i + 1; j < c; ++j) s -= A[i][j] * x[j];
+    x[i] = s / A[i][i];
+  }
+}
+
+// (w, β) = K⁻¹ [z; 0] from the factor, then two refinement steps with double-double residuals
+int global_dual_weights(gsk_ctx *ctx) {
+  GlobalPlan *g = ctx->gplan;
+  cudaStream_t st = ctx->stream;
+  const long long np = g->np;
+  const int c = ctx->es.nterms, ne = g->ne;
+  GArgs ga{ctx->d_rec_orig, g->n, np, ctx->vg, ctx->prob.dim};
+  double *y = g->tmp, *v = g->tmp + np, *r = g->tmp + 2 * np, *small = g->tmp + 3 * np;  // small: 32 doubles
+  const unsigned gw = (unsigned)((np + 7) / 8), gt = (unsigned)((np + 255) / 256);
+  double hGEE[(1 + GSK_MAX_DRIFT_TERMS) * (1 + GSK_MAX_DRIFT_TERMS)];
+  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(hGEE, g->GEE, sizeof(double) * ne * ne, cudaMemcpyDeviceToHost, st));
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  const double *Gff = hGEE + ne + 1;  // rows/cols 1… of G_EE
+  long double beta[GSK_MAX_DRIFT_TERMS] = {}, rhs[GSK_MAX_DRIFT_TERMS], d[GSK_MAX_DRIFT_TERMS];
+  double hb[GSK_MAX_DRIFT_TERMS] = {};
+  // first solution: β = Gff⁻¹ Gfz,  w = L⁻ᵀ (Y_z − Y_F β)
+  for (int j = 0; j < c; ++j) rhs[j] = hGEE[(1 + j) * ne];
+  if (c > 0) host_spd_solve(c, Gff, ne, rhs, beta);
+  for (int j = 0; j < c; ++j) hb[j] = (double)beta[j];
+  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(small, hb, sizeof(double) * GSK_MAX_DRIFT_TERMS, cudaMemcpyHostToDevice, st));
+  sub_cols_kernel<<<gt, 256, 0, st>>>(g->YE, g->YE, np, c, small, v);
+  xt_matvec_kernel<<<gw, 256, 0, st>>>(g->X, np, np, v, g->w);
+  for (int it = 0; it < 2; ++it) {
+    // residuals: r_w = z − C w − F β (double-double), r_β = −Fᵀ w
+    switch (ctx->vg.kind) {
+      case GSK_VARIO_GAUSSIAN: dual_residual_kernel<GSK_VARIO_GAUSSIAN><<<gw, 256, 0, st>>>(ga, g->E, ne, g->w, ctx->es, small, r); break;
+      case GSK_VARIO_SPHERICAL: dual_residual_kernel<GSK_VARIO_SPHERICAL><<<gw, 256, 0, st>>>(ga, g->E, ne, g->w, ctx->es, small, r); break;
+      default: dual_residual_kernel<GSK_VARIO_EXPONENTIAL><<<gw, 256, 0, st>>>(ga, g->E, ne, g->w, ctx->es, small, r); break;
+    }
+    double hrb[GSK_MAX_DRIFT_TERMS] = {}, ht[GSK_MAX_DRIFT_TERMS] = {};
+    if (c > 0) {
+      cols_dot_dd_kernel<<<c, 256, 0, st>>>(g->E + np, np, np, g->w, small + 16);  // Fᵀ w
+      GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(hrb, small + 16, sizeof(double) * c, cudaMemcpyDeviceToHost, st));
+    }
+    // δ: y = L⁻¹ r_w;  δβ = Gff⁻¹ (Y_Fᵀ y + Fᵀw);  δw = L⁻ᵀ (y − Y_F δβ)
+    linv_times_e_kernel<<<gw, 256, 0, st>>>(g->X, np, np, r, 1, y);
+    if (c > 0) {
+      cols_dot_dd_kernel<<<c, 256, 0, st>>>(g->YE + np, np, np, y, small + 16);
+      GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(ht, small + 16, sizeof(double) * c, cudaMemcpyDeviceToHost, st));
+      GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+      for (int j = 0; j < c; ++j) rhs[j] = (long double)ht[j] + (long double)hrb[j];  // t − r_β with r_β = −Fᵀw
+      host_spd_solve(c, Gff, ne, rhs, d);
+      double hd[GSK_MAX_DRIFT_TERMS] = {};
+      for (int j = 0; j < c; ++j) { hd[j] = (double)d[j]; beta[j] += d[j]; hb[j] = (double)beta[j]; }
+      GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(small + 16, hd, sizeof(double) * GSK_MAX_DRIFT_TERMS, cudaMemcpyHostToDevice, st));
+      sub_cols_kernel<<<gt, 256, 0, st>>>(y, g->YE, np, c, small + 16, v);
+      xt_matvec_kernel<<<gw, 256, 0, st>>>(g->X, np, np, v, r);
+      GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));  // hd leaves scope
+      GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(small, hb, sizeof(double) * GSK_MAX_DRIFT_TERMS, cudaMemcpyHostToDevice, st));
+    } else {
+      xt_matvec_kernel<<<gw, 256, 0, st>>>(g->X, np, np, y, r);
+    }
+    axpy_kernel<<<gt, 256, 0, st>>>(g->w, r, np);
+    GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  }
+  for (int j = 0; j < GSK_MAX_DRIFT_TERMS; ++j) g->beta[j] = (j < c) ? (double)beta[j] : 0.0;
+  GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  return GSK_OK;
+}
+}  // namespace
 
 void gsk_global_free(gsk_ctx *ctx) {
   GlobalPlan *g = ctx->gplan;
@@ -660,6 +873,9 @@ int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const doub
   linv_times_e_kernel<<<(unsigned)((np + 7) / 8), 256, 0, st>>>(g->X, np, np, g->E, g->ne, g->YE);
   gram_ee_kernel<<<1, 256, 0, st>>>(g->YE, np, g->ne, g->GEE);
   GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  if ((rc = gsk_buf(ctx, BUF_G_W, sizeof(double) * (size_t)np, (void **)&g->w)) != GSK_OK) return rc;
+  if ((rc = gsk_buf(ctx, BUF_G_TMP, sizeof(double) * (size_t)(3 * np + 32), (void **)&g->tmp)) != GSK_OK) return rc;
+  if ((rc = global_dual_weights(ctx)) != GSK_OK) return rc;
 
   // batch of targets per GEMM: bound B to ~2 GB (the buffers are sized in gsk_global_execute)
   long long batch = (long long)((2.0e9 / 8.0) / (double)np);
@@ -681,7 +897,7 @@ int gsk_global_update_values(gsk_ctx *ctx) {
   linv_times_e_kernel<<<(unsigned)((np + 7) / 8), 256, 0, st>>>(g->X, np, np, g->E, g->ne, g->YE);
   gram_ee_kernel<<<1, 256, 0, st>>>(g->YE, np, g->ne, g->GEE);
   GSK_CUDA_CHECK(ctx, cudaGetLastError());
-  return GSK_OK;
+  return global_dual_weights(ctx);
 }
 
 int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, int *d_nn, int *launches) {
@@ -696,7 +912,11 @@ int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, int *d_nn
     int rc;
     if ((rc = gsk_buf(ctx, BUF_G_BM, sizeof(double) * (size_t)np * bmax, (void **)&g->Bm)) != GSK_OK) return rc;
     if ((rc = gsk_buf(ctx, BUF_G_PARTIAL, sizeof(double) * (size_t)(np / GT) * (1 + g->ne) * g->batch, (void **)&g->partial)) != GSK_OK) return rc;
+    if ((rc = gsk_buf(ctx, BUF_G_DMEAN, sizeof(double) * (size_t)g->batch, (void **)&g->dmean)) != GSK_OK) return rc;
   }
+  GDual dual{};
+  dual.dmean = g->dmean;
+  for (int j = 0; j < GSK_MAX_DRIFT_TERMS; ++j) dual.beta[j] = g->beta[j];
   for (long long off = 0; off < count; off += g->batch) {
     const int nb = (int)std::min<long long>(g->batch, count - off);
     const int nbp = (nb + GT - 1) / GT * GT;
@@ -719,12 +939,13 @@ int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, int *d_nn
       out_b.mean[p] += off;
       out_b.var[p] += off;
     }
+    dual_mean_kernel<<<(unsigned)((nb + 7) / 8), 256, 0, st>>>(g->Bm, np, nb, g->w, g->dmean);
     ygemm_dmma_kernel<<<dim3((unsigned)(nbp / GT), (unsigned)(np / GT)), 256, YGEMM_SMEM, st>>>(
         g->X, np, g->Bm, g->YE, g->ne, g->batch, g->partial);
     global_epilogue_kernel<<<(nb + 127) / 128, 128, 0, st>>>(g->partial, (int)(np / GT), g->ne, g->batch, nb, g->GEE, ctx->es,
                                                              ctx->tg, ctx->vg.sill, ctx->prob.flags, first + off,
-                                                             out_b);
-    if (launches) *launches += 3;
+                                                             out_b, dual);
+    if (launches) *launches += 4;
   }
   if (d_nn) {
     fill_int_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(d_nn, count, (int)g->n);

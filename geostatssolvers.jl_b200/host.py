@@ -714,4 +714,7 @@ def solve(problem: EstimationProblem, solver, ctx: Optional[_abi.Context] = None
         return _solve_kriging(problem, solver, ctx, path_order)
     if isinstance(solver, _SimpleSolver):
         return _solve_simple(problem, solver, ctx, path_order)
+    from . import simulation as _sim
+    if isinstance(solver, _sim.FFTGS):
+        return _sim.solve_fftgs(problem, solver, ctx)
     raise TypeError(f"solve: unsupported solver {type(solver).__name__}")

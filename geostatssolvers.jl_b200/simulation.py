@@ -1,0 +1,190 @@
+"""Host-side mirror of the reference's FFT Gaussian simulation solver — the first CALLER of the Kriging hot path
+(SURVEY §8f-2): ref src/simulation/fft.jl.
+
+    preprocess  fft.jl:62-135   spectrum of the covariance (one FFT), and for CONDITIONAL simulation one Simple Kriging
+                                solve of the data onto `PointSet(centroid.(pdomain))` (fft.jl:112-126)
+    solvesingle fft.jl:145-192  per realisation: random phases → inverse FFT → rescale; conditioning solves THE SAME
+                                Simple Kriging problem again with the unconditional realisation's values at the data
+                                cells (fft.jl:175-188) and adds the residual field
+
+What runs where: the FFTs go through torch.fft (cuFFT — a library call; they are not the hot path this repository
+accelerates), the Kriging solves through libgskrige.so with GSK_FLAG_REUSE_PLAN — the per-realisation solves share the
+sample coordinates, so only the VALUES cross the ABI (gsk_update_values inside gsk_krige): bins / neighbour lists
+(local) or L and L^-1 (global) stay resident in HBM between realisations.
+
+Julia's RNG cannot be reproduced here: `rng` is a numpy Generator (or a seed); the uniform noise field of a
+realisation can also be passed explicitly (`noise=`), which is what the parity tests do.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from . import _abi
+from .host import (CartesianGrid, Euclidean, GaussianVariogram, GeoTable, KBallSearch, PointSet, UnsupportedOption, _Variogram,
+                   _unsupported, default_context, georef, searcher_ui)
+
+
+class SimulationProblem:
+    """``SimulationProblem(domain, "z", nreals)`` or ``SimulationProblem(samples, domain, "z", nreals)``
+    (GeoStatsBase; ref test/simulation/fft.jl:4,33)."""
+
+    def __init__(self, *args):
+        if isinstance(args[0], GeoTable):
+            self._data, self._domain, self._var, self._nreals = args
+        else:
+            self._data = None
+            self._domain, self._var, self._nreals = args
+        self._var = self._var if isinstance(self._var, str) else self._var[0]
+
+    def data(self):
+        return self._data
+
+    def domain(self):
+        return self._domain
+
+    def variables(self):
+        return (self._var,)
+
+    def nreals(self):
+        return int(self._nreals)
+
+
+_FFTGS_DEFAULTS = dict(variogram=None, mean=0.0, minneighbors=1, maxneighbors=None, neighborhood=None, distance=None)
+
+
+class FFTGS:
+    """``FFTGS(z=dict(variogram=GaussianVariogram(range=10.0)), rng=2019)`` — parameters: ref fft.jl:50-59."""
+
+    def __init__(self, *pairs, rng=None, **kwpairs):
+        self.vparams = {}
+        for item in list(pairs) + list(kwpairs.items()):
+            for var, params in (list(item.items()) if isinstance(item, dict) else [item]):
+                unknown = set(params) - set(_FFTGS_DEFAULTS)
+                if unknown:
+                    raise TypeError(f"unknown FFTGS parameter(s) {sorted(unknown)} for variable {var}")
+                self.vparams[var] = dict(params)
+        self.rng = rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
+
+    def params(self, var):
+        p = dict(_FFTGS_DEFAULTS)
+        p.update(self.vparams.get(var, {}))
+        if p["variogram"] is None:
+            p["variogram"] = GaussianVariogram()
+        if p["distance"] is None:
+            p["distance"] = Euclidean()
+        return p
+
+
+def variogram_values(gamma: _Variogram, h: np.ndarray) -> np.ndarray:
+    """γ(h), point to point (Variography formulas) — host side, for the spectrum only."""
+    h = np.asarray(h, dtype=np.float64)
+    s, r = gamma.sill, gamma.range
+    n = gamma.nugget + (1e-6 if gamma.kind == _abi.VARIO_GAUSSIAN else 0.0)
+    if gamma.kind == _abi.VARIO_GAUSSIAN:
+        g = (s - n) * (1.0 - np.exp(-3.0 * (h / r) ** 2))
+    elif gamma.kind == _abi.VARIO_SPHERICAL:
+        t = h / r
+        g = np.where(h < r, (s - n) * (1.5 * t - 0.5 * t ** 3), (s - n))
+    else:
+        g = (s - n) * (1.0 - np.exp(-3.0 * (h / r)))
+    return g + np.where(h > 0, n, 0.0)
+
+
+def _fft_device():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("FFTGS runs its FFTs on the GPU (torch.fft / cuFFT); no CUDA device is visible")
+    return torch, torch.device("cuda", torch.cuda.current_device())
+
+
+def _kriging_spec(gamma, mean, p, data_coords, data_vals, target_pts):
+    """SK of the data onto PointSet(centroid.(pdomain)) — the KrigingSolver of fft.jl:115-124 as a ProblemSpec."""
+    if not isinstance(p["distance"], Euclidean):
+        raise _unsupported("non-Euclidean `distance`")
+    n = data_vals.shape[0]
+    dim = len(data_coords)
+    sdom = PointSet(np.stack(data_coords, 0))
+    kw = dict(coords=data_coords, values=data_vals, points=target_pts, vario_kind=gamma.kind, vario_range=gamma.range,
+              vario_sill=gamma.sill, vario_nugget=gamma.nugget, estimator=_abi.EST_SIMPLE, sk_mean=float(mean),
+              min_neighbors=int(p["minneighbors"]), flags=_abi.FLAGS_DEFAULT | _abi.FLAG_REUSE_PLAN)
+    if p["maxneighbors"] is not None:                                  # krig.jl:151: local iff maxneighbors given
+        searcher = searcher_ui(sdom, p["maxneighbors"], p["distance"], p["neighborhood"])
+        if searcher.k > _abi.GSK_MAX_NEIGHBORS:
+            raise _unsupported(f"maxneighbors > {_abi.GSK_MAX_NEIGHBORS} on the local path")
+        kw.update(max_neighbors=searcher.k)
+        if isinstance(searcher, KBallSearch):
+            kw.update(ball_radius=searcher.ball.radius())
+    del n, dim
+    return _abi.ProblemSpec(**kw)
+
+
+def preprocess_fftgs(problem: SimulationProblem, solver: FFTGS, ctx: Optional[_abi.Context] = None) -> dict:
+    """ref fft.jl:62-135"""
+    pgrid = problem.domain()
+    if not isinstance(pgrid, CartesianGrid):
+        raise _unsupported("FFTGS on a domain that is not a CartesianGrid")
+    torch, dev = _fft_device()
+    dims = pgrid.dims
+    var = problem.variables()[0]
+    p = solver.params(var)
+    gamma, mu = p["variogram"], float(p["mean"])
+    if not isinstance(gamma, _Variogram) or gamma.kind < 0:
+        raise _unsupported(f"variogram {type(gamma).__name__}")
+    cents = pgrid.centroids()                                          # x fastest
+    cidx = [d // 2 - 1 for d in dims]                                  # CartesianIndex(dims .÷ 2), 0-based (fft.jl:69)
+    ccen = [pgrid.origin[a] + (max(cidx[a], 0) + 0.5) * pgrid.spacing[a] for a in range(len(dims))]
+    h = np.sqrt(sum((cents[a] - ccen[a]) ** 2 for a in range(len(dims))))
+    cov = gamma.sill - variogram_values(gamma, h)                      # fft.jl:98-100
+    C = torch.from_numpy(np.reshape(cov, dims, order="F").copy()).to(dev)
+    F = torch.sqrt(torch.abs(torch.fft.fftn(torch.fft.fftshift(C))))   # fft.jl:103
+    F.view(-1)[0] = 0.0                                                # fft.jl:104: F[1] = 0 (Julia's first element)
+    pre = dict(gamma=gamma, mu=mu, F=F, zbar=None, spec=None, dinds=None, p=p, dims=dims, cents=cents)
+    pdata = problem.data()
+    if pdata is not None and var in pdata.table:                       # fft.jl:108-134
+        ddom = pdata.domain
+        if not isinstance(ddom, PointSet):
+            raise _unsupported("sample domains that are not point sets")
+        dcoords = ddom.centroids()
+        dvals = np.asarray(pdata.table[var], dtype=np.float64)
+        spec = _kriging_spec(gamma, mu, p, dcoords, dvals, cents)
+        zbar, _ = (ctx or default_context()).krige(spec)               # fft.jl:125-126
+        # nearest grid element of every datum (KNearestSearch(pdomain, 1), fft.jl:129-133); unique, first occurrence
+        ijk = [np.clip(np.floor((dcoords[a] - pgrid.origin[a]) / pgrid.spacing[a]).astype(np.int64), 0, dims[a] - 1)
+               for a in range(len(dims))]
+        lin = np.zeros_like(ijk[0])
+        for a in reversed(range(len(dims))):
+            lin = lin * dims[a] + ijk[a]
+        _, first = np.unique(lin, return_index=True)
+        pre.update(zbar=zbar, dinds=lin[np.sort(first)])
+    return pre
+
+
+def solvesingle_fftgs(problem: SimulationProblem, solver: FFTGS, pre: dict, ctx: Optional[_abi.Context] = None,
+                      noise: Optional[np.ndarray] = None) -> np.ndarray:
+    """ref fft.jl:145-192 — one realisation (a flat array in domain order)."""
+    torch, dev = _fft_device()
+    dims, gamma, mu, F = pre["dims"], pre["gamma"], pre["mu"], pre["F"]
+    if noise is None:
+        noise = solver.rng.random(dims[::-1]).transpose()              # rand(rng, V, dims), column-major fill
+    U = torch.from_numpy(np.ascontiguousarray(np.reshape(np.asarray(noise, dtype=np.float64), dims))).to(dev)
+    P = F * torch.exp(1j * torch.angle(torch.fft.fftn(U)))             # fft.jl:161
+    Z = torch.real(torch.fft.ifftn(P))                                 # fft.jl:164
+    s2 = torch.mean(Z * Z) * (Z.numel() / (Z.numel() - 1))             # Statistics.var(Z, mean=0): corrected (fft.jl:167)
+    Z = torch.sqrt(gamma.sill / s2) * Z + mu                           # fft.jl:168
+    zu = Z.cpu().numpy().reshape(-1, order="F")                        # Z[inds], x fastest
+    if pre["zbar"] is None:
+        return zu
+    dinds = pre["dinds"]
+    cents = pre["cents"]
+    spec = _kriging_spec(gamma, mu, pre["p"], [c[dinds] for c in cents], zu[dinds].copy(), cents)   # fft.jl:176-186
+    zbar_u, _ = (ctx or default_context()).krige(spec)                 # same coordinates every realisation: values-only update
+    return pre["zbar"] + (zu - zbar_u)                                 # fft.jl:189
+
+
+def solve_fftgs(problem: SimulationProblem, solver: FFTGS, ctx: Optional[_abi.Context] = None):
+    """``solve(problem, FFTGS(...))`` — a list of `nreals` GeoTables (the reference returns an Ensemble)."""
+    pre = preprocess_fftgs(problem, solver, ctx)
+    var = problem.variables()[0]
+    return [georef({var: solvesingle_fftgs(problem, solver, pre, ctx)}, problem.domain()) for _ in range(problem.nreals())]

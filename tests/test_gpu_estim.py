@@ -205,3 +205,73 @@ def test_uk2_3d_k96_large_support_fits_or_reports(gsk, ctx, oracle):
     om, ov, onn, oidx = oracle.krige(spec, want_neighbors=True)
     assert np.array_equal(idx, oidx)
     assert_parity(mean, var, om, ov, atol_mean=1e-6, atol_var=1e-6)  # k = 96, UK2: cond·eps floor as in test_more_edge_shapes
+
+
+# ---- the first caller of the Kriging path: FFT Gaussian simulation with conditioning (ref src/simulation/fft.jl) ----
+def _numpy_fftgs(gsk, oracle, grid, gamma, mu, data_coords, data_vals, noises, maxneighbors=None):
+    """fft.jl:62-192 restated with numpy FFTs and the CPU oracle for the two Kriging solves"""
+    from gskrige.simulation import variogram_values
+    dims = grid.dims
+    cents = grid.centroids()
+    ccen = [grid.origin[a] + (dims[a] // 2 - 1 + 0.5) * grid.spacing[a] for a in range(len(dims))]
+    h = np.sqrt(sum((cents[a] - ccen[a]) ** 2 for a in range(len(dims))))
+    C = np.reshape(gamma.sill - variogram_values(gamma, h), dims, order="F")
+    F = np.sqrt(np.abs(np.fft.fftn(np.fft.fftshift(C))))
+    F.flat[0] = 0.0
+
+    def sk(coords, vals):
+        spec = gsk.ProblemSpec(coords=coords, values=vals, points=cents, vario_kind=gamma.kind, vario_range=gamma.range,
+                               vario_sill=gamma.sill, vario_nugget=gamma.nugget, estimator=gsk.EST_SIMPLE, sk_mean=mu,
+                               max_neighbors=maxneighbors or 0)
+        return oracle.krige(spec)[0]
+
+    zbar = sk(data_coords, data_vals)
+    ijk = [np.clip(np.floor((data_coords[a] - grid.origin[a]) / grid.spacing[a]).astype(np.int64), 0, dims[a] - 1) for a in range(len(dims))]
+    lin = ijk[0] + dims[0] * ijk[1]
+    _, first = np.unique(lin, return_index=True)
+    dinds = lin[np.sort(first)]
+    out = []
+    for U in noises:
+        P = F * np.exp(1j * np.angle(np.fft.fftn(U)))
+        Z = np.real(np.fft.ifftn(P))
+        Z = np.sqrt(gamma.sill / (np.sum(Z * Z) / (Z.size - 1))) * Z + mu
+        zu = Z.reshape(-1, order="F")
+        out.append(zbar + (zu - sk([c[dinds] for c in cents], zu[dinds].copy())))
+    return out, dinds
+
+
+@pytest.mark.parametrize("maxneighbors", [None, 3])
+def test_fftgs_conditional_simulation(gsk, oracle, maxneighbors):
+    """ref test/simulation/fft.jl:27-37 (conditional simulation on CartesianGrid(100,100), three data; here 40×30 so that
+    the oracle's global solves stay small) with explicit noise fields, against the numpy + oracle restatement"""
+    grid = gsk.CartesianGrid(40, 30)
+    gamma = gsk.GaussianVariogram(range=10.0)
+    dcoords = [np.array([10.0, 20.2, 30.7, 5.5, 20.9]), np.array([10.0, 22.4, 14.1, 25.5, 22.1])]   # two data share a cell
+    dvals = np.array([1.0, -1.0, 1.0, 0.3, -0.7])
+    data = gsk.georef({"z": dvals}, np.stack(dcoords, 0))
+    rng = np.random.default_rng(2022)
+    noises = [rng.random(grid.dims) for _ in range(3)]
+    params = dict(variogram=gamma) if maxneighbors is None else dict(variogram=gamma, maxneighbors=maxneighbors)
+    solver = gsk.FFTGS(z=params, rng=1)
+    problem = gsk.SimulationProblem(data, grid, "z", 3)
+    with gsk.Context(0) as c:
+        pre = gsk.simulation.preprocess_fftgs(problem, solver, c)
+        want, dinds = _numpy_fftgs(gsk, oracle, grid, gamma, 0.0, dcoords, dvals, noises, maxneighbors)
+        assert np.array_equal(pre["dinds"], dinds) and len(dinds) == 4
+        plans = []
+        for U, w in zip(noises, want):
+            z = gsk.simulation.solvesingle_fftgs(problem, solver, pre, c, noise=U)
+            plans.append(c.timing()["ms_plan"])
+            # cuFFT vs pocketfft: 1e-13 relative on the field; the Gaussian SK systems amplify by their condition number
+            np.testing.assert_allclose(z, w, rtol=1e-7, atol=1e-7)
+            # conditioning: the simulated field honours the data at the data cells' centroids in expectation only
+            # (fft.jl conditions on cell centroids); what must hold exactly is z = zbar + (zu - zbar_u) at every cell
+            assert np.all(np.isfinite(z))
+        assert plans[0] > 0 and plans[1] == 0 and plans[2] == 0      # realisations 2, 3: same coordinates → values only
+        sols = gsk.solve(problem, solver, ctx=c)
+        assert len(sols) == 3 and sols[0].z.shape == (1200,)
+    # unconditional: realisations are rescaled to the sill
+    sols = gsk.solve(gsk.SimulationProblem(grid, "z", 2), gsk.FFTGS(z=dict(variogram=gamma), rng=3))
+    for s in sols:
+        z = np.asarray(s.z)
+        assert abs(np.sum(z * z) / (z.size - 1) - 1.0) < 1e-9

@@ -474,3 +474,24 @@ def test_full_size_random_and_sample_cells(gsk, ctx, oracle, name):
     lin = int(cells[0][0] + g[0] * (cells[1][0] + g[1] * cells[2][0]))
     gm, gv = ctx.krige(spec.with_slab(lin, 1))[:2]
     np.testing.assert_allclose([gm[0], gv[0]], [mean[0], var[0]], rtol=1e-12, atol=1e-14)
+
+
+def test_config_c4_full_size_golden(gsk, ctx):
+    """C4 at FULL size (20 000 samples, the 20 001² system) against 4 096 golden targets solved with LAPACK
+    dsytrf/dsytrs — the factorisation the reference itself calls — by tests/golden/make_golden_c4.py. The golden
+    targets are reached through a traversal order that visits them first (the slab is then the first 4 096 positions)."""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "c4_full_4096.npz")
+    spec = gsk.synth.config_spec("C4")
+    T = spec.n_targets
+    chosen = g["targets"]
+    rest = np.setdiff1d(np.arange(T, dtype=np.int64), chosen, assume_unique=True)
+    import copy
+    sp = copy.copy(spec)
+    sp.target_order = np.concatenate([chosen, rest])
+    mean, var = ctx.krige(sp.with_slab(0, chosen.size))
+    # Spherical(r = 256) on 20 000 samples: cond(C) ~ 1e6-1e7; Bunch–Kaufman on the indefinite (n+1)-system and
+    # Cholesky + Schur complement on L⁻¹ are both backward stable, so they agree to ~cond·eps ≈ 1e-9 in the mean
+    # (values of order 1): rtol 1e-9 with that absolute floor (north_star's tolerance, floor stated per SURVEY §8d)
+    np.testing.assert_allclose(mean, g["mean"], rtol=1e-9, atol=2e-9)
+    np.testing.assert_allclose(var, g["var"], rtol=1e-9, atol=2e-9)
