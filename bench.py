@@ -222,8 +222,10 @@ class Env:
             raise SystemExit("bench.py needs a B200: the Kriging path has no CPU fallback")
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        self.cpu_group = None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
+            self.cpu_group = dist.new_group(backend="gloo")   # host-only barrier: an NCCL barrier keeps a kernel spinning on the waiting GPUs
         self.stream = torch.cuda.current_stream()
         self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=self.dev)   # 256 MB > 126 MB L2
         self.peaks = None
@@ -490,6 +492,32 @@ def main():
     roof = w.roofline(ms_per_step, solve_ms, search_ms, launches, dfma, dmma)
     spec, job, count, plan_ms, gather_mode = w.spec, w.job, w.count, w.plan_ms, w.gather_mode
     w.close()
+
+    # N > 1, additionally: the whole job through ONE call of the single-process multi-GPU entry point (gsk_krige_multi —
+    # what a Julia host driving all GPUs of the box from one process uses): rank 0 calls it over all N devices while the
+    # other ranks idle at the barrier. Host buffers are page-locked; sample upload, bin build, kernels and the copies
+    # back are inside the timed region.
+    if env.world > 1:
+        if env.rank == 0:
+            try:
+                hm = torch.empty(job[1], dtype=torch.float64).pin_memory().numpy()
+                hv = torch.empty(job[1], dtype=torch.float64).pin_memory().numpy()
+                whole = spec.with_slab(job[0], job[1])
+                env.gsk.krige_multi(whole, list(range(env.world)), out=(hm, hv))      # warm: contexts, buffers
+                reps = 1 if long_step else 3
+                m0 = time.perf_counter()
+                for _ in range(reps):
+                    env.gsk.krige_multi(whole, list(range(env.world)), out=(hm, hv))
+                ms = (time.perf_counter() - m0) / reps * 1e3
+                e2e["single_process"] = {"value": job[1] / (ms * 1e-3), "ms_per_step": ms, "steps": reps,
+                                         "api": "gsk_krige_multi (one process, one host thread and context per GPU, page-locked host buffers)"}
+                del hm, hv
+            except Exception as exc:  # noqa: BLE001 - informational leg
+                e2e["single_process"] = {"error": f"{type(exc).__name__}: {exc}"}
+        # the other ranks wait on the HOST (gloo): a waiting NCCL barrier is a spinning kernel on their GPUs, and a GPU
+        # time-slices between the processes that use it — rank 0's worker for that device would run at half speed
+        dist.barrier(group=env.cpu_group)
+        env.barrier()
 
     configs = {}
     if not args.no_secondary and not args.targets:

@@ -301,9 +301,10 @@ class Context:
         self.device = device
 
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
-            self.lib.gsk_destroy(self._h)
-            self._h = C.c_void_p()
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self.lib.gsk_destroy(h)
+            self._h = None          # (module globals such as `C` may already be gone at interpreter shutdown)
 
     __del__ = close
 
@@ -388,12 +389,14 @@ class Context:
         return a.value, b.value
 
 
-def krige_multi(spec: ProblemSpec, device_ids, want_neighbors: bool = False):
-    """Single-process multi-GPU call (``gsk_krige_multi``): the slab is split over ``device_ids``."""
+def krige_multi(spec: ProblemSpec, device_ids, want_neighbors: bool = False, out=None):
+    """Single-process multi-GPU call (``gsk_krige_multi``): the slab is split over ``device_ids``.
+    ``out=(mean, var)``: caller-provided (e.g. page-locked) float64 arrays of the slab length."""
     lib = load_library()
     first, count = spec.slab
-    mean = np.empty(count, dtype=np.float64)
-    var = np.empty(count, dtype=np.float64)
+    mean, var = out if out is not None else (np.empty(count, dtype=np.float64), np.empty(count, dtype=np.float64))
+    if mean.shape != (count,) or var.shape != (count,) or mean.dtype != np.float64 or var.dtype != np.float64:
+        raise ValueError("out arrays must be float64 of the slab length")
     k = spec.params["max_neighbors"]
     nneigh = np.empty(count, dtype=np.int32) if want_neighbors else None
     idx = np.empty((count, max(k, 1)), dtype=np.int32) if (want_neighbors and k > 0) else None

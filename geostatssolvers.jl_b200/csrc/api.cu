@@ -194,6 +194,7 @@ extern "C" GSK_API void gsk_destroy(gsk_ctx *ctx) {
   free_plan(ctx);
   for (int i = 0; i < BUF_COUNT; ++i) cudaFree(ctx->bufp[i]);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->h_out) cudaFreeHost(ctx->h_out);
   cudaFree(ctx->d_nn);
   cudaFree(ctx->d_nbr);
   cudaFree(ctx->d_nn_out);
@@ -814,6 +815,66 @@ static int krige_pieces(gsk_ctx *ctx, const gsk_problem *p, int64_t first, int64
     cudaStreamSynchronize(ctx->stream);
     return code;
   };
+  // Are the caller's arrays page-locked? A plain Julia Vector / numpy array is not, and an asynchronous device→host
+  // copy into pageable memory degenerates into a slow blocking one (measured: 8× the whole call on C5 slabs). Pageable
+  // outputs are therefore filled through two page-locked 8 MB staging buffers: DMA into one while the host copies the
+  // other out; piece i is drained while the kernels of piece i+1 — already enqueued — run.
+  auto is_pinned = [](const void *ptr) {
+    if (!ptr) return true;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+  };
+  const bool pinned = is_pinned(mean_out) && is_pinned(var_out) && is_pinned(nneigh_out) && is_pinned(neigh_idx_out);
+  constexpr size_t STG = (size_t)8 << 20;
+  char *stg[2] = {nullptr, nullptr};
+  if (!pinned) {
+    if (ctx->h_out_cap < 2 * STG) {
+      if (ctx->h_out) cudaFreeHost(ctx->h_out);
+      ctx->h_out = nullptr;
+      ctx->h_out_cap = 0;
+      if (cudaHostAlloc(&ctx->h_out, 2 * STG, cudaHostAllocDefault) != cudaSuccess)
+        return fail(ctx, GSK_ERR_NOMEM, "pinned staging allocation failed");
+      ctx->h_out_cap = 2 * STG;
+    }
+    stg[0] = (char *)ctx->h_out;
+    stg[1] = (char *)ctx->h_out + STG;
+  }
+  struct Pend { char *dst; size_t bytes; bool live; } pend[2] = {{nullptr, 0, false}, {nullptr, 0, false}};
+  int tog = 0;
+  cudaError_t ce = cudaSuccess;
+  auto flush_slot = [&](int b) {
+    if (!pend[b].live) return;
+    if (ce == cudaSuccess) ce = cudaEventSynchronize(ctx->ev_solve[b]);
+    if (ce == cudaSuccess) memcpy(pend[b].dst, stg[b], pend[b].bytes);
+    pend[b].live = false;
+  };
+  auto staged_copy = [&](void *dst, const void *src, size_t bytes) {
+    for (size_t o = 0; o < bytes && ce == cudaSuccess; o += STG) {
+      const size_t nb = std::min(STG, bytes - o);
+      flush_slot(tog);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(stg[tog], (const char *)src + o, nb, cudaMemcpyDeviceToHost, ctx->stream2);
+      if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_solve[tog], ctx->stream2);
+      pend[tog] = {(char *)dst + o, nb, true};
+      tog ^= 1;
+    }
+  };
+  auto copy_piece = [&](long long off, long long cnt) {  // stream2 already waits for the piece's kernels
+    if (pinned) {
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(mean_out + off, d_mean + off, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(var_out + off, d_var + off, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2);
+      if (ce == cudaSuccess && d_nn)
+        ce = cudaMemcpyAsync(nneigh_out + off, d_nn + off, sizeof(int) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2);
+      if (ce == cudaSuccess && d_idx)
+        ce = cudaMemcpyAsync(neigh_idx_out + off * k, d_idx + off * k, sizeof(int) * (size_t)cnt * k, cudaMemcpyDeviceToHost, ctx->stream2);
+      return;
+    }
+    staged_copy(mean_out + off, d_mean + off, sizeof(double) * (size_t)cnt);
+    staged_copy(var_out + off, d_var + off, sizeof(double) * (size_t)cnt);
+    if (d_nn) staged_copy(nneigh_out + off, d_nn + off, sizeof(int) * (size_t)cnt);
+    if (d_idx) staged_copy(neigh_idx_out + off * k, d_idx + off * k, sizeof(int) * (size_t)cnt * k);
+  };
+  long long prev_off = -1, prev_cnt = 0;
   for (int pi = 0; pi < npieces; ++pi) {
     const long long off = bounds[pi], cnt = bounds[pi + 1] - bounds[pi];
     if (cnt <= 0) continue;
@@ -821,21 +882,33 @@ static int krige_pieces(gsk_ctx *ctx, const gsk_problem *p, int64_t first, int64
                      d_idx ? d_idx + off * k : nullptr);
     if (rc != GSK_OK) return drain(rc);
     const int eb = pi & 1;
-    cudaError_t ce = cudaEventRecord(ctx->ev_search[eb], ctx->stream);  // "piece done" marker
-    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stream2, ctx->ev_search[eb], 0);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(mean_out + off, d_mean + off, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2);
-    if (ce == cudaSuccess) ce = cudaMemcpyAsync(var_out + off, d_var + off, sizeof(double) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2);
-    if (ce == cudaSuccess && d_nn)
-      ce = cudaMemcpyAsync(nneigh_out + off, d_nn + off, sizeof(int) * (size_t)cnt, cudaMemcpyDeviceToHost, ctx->stream2);
-    if (ce == cudaSuccess && d_idx)
-      ce = cudaMemcpyAsync(neigh_idx_out + off * k, d_idx + off * k, sizeof(int) * (size_t)cnt * k, cudaMemcpyDeviceToHost, ctx->stream2);
+    if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_search[eb], ctx->stream);  // "piece done" marker
+    if (pinned) {
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stream2, ctx->ev_search[eb], 0);
+      copy_piece(off, cnt);
+    } else {
+      // the previous piece's results leave while this piece's kernels run (its marker was recorded a round ago)
+      if (prev_off >= 0) copy_piece(prev_off, prev_cnt);
+      if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ctx->stream2, ctx->ev_search[eb], 0);
+      prev_off = off;
+      prev_cnt = cnt;
+    }
+    if (ce != cudaSuccess) {
+      ctx->err = std::string("gsk_krige: result copy failed: ") + cudaGetErrorString(ce);
+      return drain(GSK_ERR_CUDA);
+    }
+  }
+  if (!pinned) {
+    if (prev_off >= 0) copy_piece(prev_off, prev_cnt);
+    flush_slot(0);
+    flush_slot(1);
     if (ce != cudaSuccess) {
       ctx->err = std::string("gsk_krige: result copy failed: ") + cudaGetErrorString(ce);
       return drain(GSK_ERR_CUDA);
     }
   }
   ctx->timing.targets = count;
-  cudaError_t ce = cudaStreamSynchronize(ctx->stream2);
+  ce = cudaStreamSynchronize(ctx->stream2);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
   if (ce == cudaSuccess) ce = cudaGetLastError();
   if (ce != cudaSuccess) {

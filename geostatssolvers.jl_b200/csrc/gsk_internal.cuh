@@ -189,6 +189,8 @@ struct gsk_ctx {
   size_t bufcap[BUF_COUNT] = {};
   void *h_stage = nullptr;  // pinned host staging buffer
   size_t h_stage_cap = 0;
+  void *h_out = nullptr;    // two pinned 8 MB buffers through which results reach pageable caller arrays
+  size_t h_out_cap = 0;
 
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   gsk_timing timing{};
