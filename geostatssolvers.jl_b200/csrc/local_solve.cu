@@ -42,10 +42,11 @@ int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long 
   cudaError_t err;
   static const bool no_small = GSK_DEV_ENV("GSK_NO_SMALL_KERNEL") != nullptr;  // development switch
   static const int cfg32 = GSK_DEV_ENV("GSK_CFG_K32") ? atoi(GSK_DEV_ENV("GSK_CFG_K32")) : 0;  // development switch
-  static const int wpt_min_k = GSK_DEV_ENV("GSK_WPT_MIN_K") ? atoi(GSK_DEV_ENV("GSK_WPT_MIN_K")) : 32;  // development switch
+  static const int wpt2_min_k = GSK_DEV_ENV("GSK_WPT2_MIN_K") ? atoi(GSK_DEV_ENV("GSK_WPT2_MIN_K")) : 21;  // development switch
   if (!no_small && a.k <= gsk_local::SK_KMAX && (ctx->es.kind == GSK_EST_SIMPLE || ctx->es.nterms == 1))
     err = gsk_local_launch_small(a, st);
-  else if (a.k > wpt_min_k && a.k <= 64 && e <= 8) err = gsk_local_launch_wpt(a, e, st);  // block-pool kernel (C5: k = 64)
+  else if (a.k > 32 && a.k <= 64 && e <= 8) err = gsk_local_launch_wpt(a, e, st);          // block-pool kernel, one warp per target (C5)
+  else if (a.k >= wpt2_min_k && a.k <= 32 && e <= 8) err = gsk_local_launch_wpt2(a, e, st);  // … two targets per warp (C3)
   else if (rows(4) <= 12) err = gsk_local_launch_A(a, e, st);
   else if (rows(4) <= 24) err = gsk_local_launch_B(a, e, st);
   else if (cfg32 == 1 && rows(8) <= 40) err = gsk_local_launch_C1(a, e, st);
