@@ -41,7 +41,6 @@ int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long 
   auto rows = [&](int W) { return (a.k + W - 1) / W * W + (e + W - 1) / W * W; };
   cudaError_t err;
   static const bool no_small = GSK_DEV_ENV("GSK_NO_SMALL_KERNEL") != nullptr;  // development switch
-  static const int cfg32 = GSK_DEV_ENV("GSK_CFG_K32") ? atoi(GSK_DEV_ENV("GSK_CFG_K32")) : 0;  // development switch
   static const int wpt2_min_k = GSK_DEV_ENV("GSK_WPT2_MIN_K") ? atoi(GSK_DEV_ENV("GSK_WPT2_MIN_K")) : 21;  // development switch
   if (!no_small && a.k <= gsk_local::SK_KMAX && (ctx->es.kind == GSK_EST_SIMPLE || ctx->es.nterms == 1))
     err = gsk_local_launch_small(a, st);
@@ -49,10 +48,6 @@ int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long 
   else if (a.k >= wpt2_min_k && a.k <= 32 && e <= 8) err = gsk_local_launch_wpt2(a, e, st);  // … two targets per warp (C3)
   else if (rows(4) <= 12) err = gsk_local_launch_A(a, e, st);
   else if (rows(4) <= 24) err = gsk_local_launch_B(a, e, st);
-  else if (cfg32 == 1 && rows(8) <= 40) err = gsk_local_launch_C1(a, e, st);
-  else if (cfg32 == 2 && rows(4) <= 36) err = gsk_local_launch_C2(a, e, st);
-  else if (cfg32 == 3 && rows(4) <= 36) err = gsk_local_launch_C3(a, e, st);
-  else if (cfg32 == 4 && rows(8) <= 40) err = gsk_local_launch_C4(a, e, st);
   else if (rows(8) <= 40) err = gsk_local_launch_C(a, e, st);
   else if (rows(8) <= 72) err = gsk_local_launch_D(a, e, st);
   else if (rows(8) <= 112) err = gsk_local_launch_E(a, e, st);

@@ -944,10 +944,6 @@ inline cudaError_t launch_cfg(const GskLocalArgs &a, int e, cudaStream_t st) {
 // one translation unit per register/lanes configuration (compiled in parallel)
 cudaError_t gsk_local_launch_A(const GskLocalArgs &a, int e, cudaStream_t st);  // G=4  R=3 W=4  12 rows, 128 thr
 cudaError_t gsk_local_launch_B(const GskLocalArgs &a, int e, cudaStream_t st);  // G=4  R=6 W=4  24 rows, 128 thr
-cudaError_t gsk_local_launch_C(const GskLocalArgs &a, int e, cudaStream_t st);  // G=8  R=5 W=8  40 rows, 128 thr
-cudaError_t gsk_local_launch_C1(const GskLocalArgs &a, int e, cudaStream_t st); // G=8  R=5 W=8  40 rows,  64 thr
-cudaError_t gsk_local_launch_C2(const GskLocalArgs &a, int e, cudaStream_t st); // G=8  R=5 W=4  36 rows, 128 thr
-cudaError_t gsk_local_launch_C3(const GskLocalArgs &a, int e, cudaStream_t st); // G=8  R=5 W=4  36 rows,  64 thr
-cudaError_t gsk_local_launch_C4(const GskLocalArgs &a, int e, cudaStream_t st); // G=8  R=5 W=8  40 rows,  96 thr
+cudaError_t gsk_local_launch_C(const GskLocalArgs &a, int e, cudaStream_t st);  // G=8  R=5 W=8  40 rows,  64 thr
 cudaError_t gsk_local_launch_D(const GskLocalArgs &a, int e, cudaStream_t st);  // G=32 R=3 W=8  72 rows, 128 thr
 cudaError_t gsk_local_launch_E(const GskLocalArgs &a, int e, cudaStream_t st);  // G=32 R=4 W=8 112 rows, 128 thr
