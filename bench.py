@@ -389,7 +389,9 @@ class Workload:
         traffic = None
         tf = ROOT / "profiles" / "roofline_traffic.json"
         if tf.exists():
-            traffic = json.loads(tf.read_text()).get(self.name)
+            per_target = json.loads(tf.read_text()).get("bytes_per_target", {}).get(self.name)
+            if per_target is not None and k:
+                traffic = per_target * self.count / max(1, launches // 2)   # per launch, like `achieved`'s launch set / its launches
         extra = {}
         count = self.count
         if k:

@@ -262,6 +262,11 @@ def load_library(path: os.PathLike | None = None):
     lib.gsk_execute_peers.restype = C.c_int
     lib.gsk_update_values.argtypes = [ctx, _dp, C.c_int64]
     lib.gsk_update_values.restype = C.c_int
+    lib.gsk_lu_plan.argtypes = [ctx, C.c_int, C.c_int64, C.c_int64, C.POINTER(_dp), _dp, C.c_int, C.c_double, C.c_double,
+                                C.c_double, C.c_double]
+    lib.gsk_lu_plan.restype = C.c_int
+    lib.gsk_lu_sample.argtypes = [ctx, _dp, _dp]
+    lib.gsk_lu_sample.restype = C.c_int
     lib.gsk_get_timing.argtypes = [ctx, C.POINTER(GskTiming)]
     lib.gsk_get_timing.restype = C.c_int
     lib.gsk_set_phase_timing.argtypes = [ctx, C.c_int]
@@ -283,7 +288,7 @@ def load_library(path: os.PathLike | None = None):
 
 EXPORTED_SYMBOLS = [
     "gsk_create", "gsk_destroy", "gsk_last_error", "gsk_set_stream", "gsk_synchronize", "gsk_krige", "gsk_krige_multi", "gsk_plan",
-    "gsk_execute", "gsk_execute_peers", "gsk_update_values", "gsk_get_timing", "gsk_set_phase_timing", "gsk_num_targets", "gsk_uk_exponents", "gsk_default_support",
+    "gsk_execute", "gsk_execute_peers", "gsk_update_values", "gsk_lu_plan", "gsk_lu_sample", "gsk_get_timing", "gsk_set_phase_timing", "gsk_num_targets", "gsk_uk_exponents", "gsk_default_support",
     "gsk_measure_fp64_peak", "gsk_abi_version",
 ]
 
@@ -354,6 +359,26 @@ class Context:
         """Values-only update of the planned problem (``gsk_update_values``): same coordinates, new sample values."""
         v = _as_f64(values)
         self._check(self.lib.gsk_update_values(self._h, _ptr(v), int(v.shape[0])))
+
+    # -- LU Gaussian simulation --------------------------------------------------------
+    def lu_plan(self, coords, n_data, data_values, *, vario_kind, vario_range, vario_sill=1.0, vario_nugget=0.0,
+                gaussian_nugget_eps=1e-6):
+        """coords: dim arrays of n_data + n_sim points, data locations first (``gsk_lu_plan``)."""
+        cs = [_as_f64(c) for c in coords]
+        n = cs[0].shape[0]
+        arr = (_dp * 3)(*[_ptr(cs[d]) if d < len(cs) else None for d in range(3)])
+        z = _as_f64(data_values) if n_data > 0 else None
+        self._lu_n = n
+        self._check(self.lib.gsk_lu_plan(self._h, len(cs), int(n_data), int(n - n_data), arr, _ptr(z) if z is not None else None,
+                                         int(vario_kind), float(vario_range), float(vario_sill), float(vario_nugget),
+                                         float(gaussian_nugget_eps)))
+
+    def lu_sample(self, w):
+        """one realisation for the standard normal draws ``w`` (length n_sim): the n_data + n_sim values"""
+        w = _as_f64(w)
+        y = np.empty(self._lu_n, dtype=np.float64)
+        self._check(self.lib.gsk_lu_sample(self._h, _ptr(w), _ptr(y)))
+        return y
 
     def execute(self, first, count, d_mean, d_var, d_nneigh=0, d_idx=0):
         """Device pointers (ints). Asynchronous on the context stream."""

@@ -185,6 +185,7 @@ static void free_plan(gsk_ctx *ctx) {
   ctx->nbr_cached = false;
   ctx->nbr_reuse = false;
   ctx->key_valid = false;
+  ctx->lu_n = 0;  // the LU simulation plan shares the buffers
 }
 
 extern "C" GSK_API void gsk_destroy(gsk_ctx *ctx) {
@@ -305,6 +306,22 @@ static int validate(gsk_ctx *ctx, const gsk_problem *p) {
   return GSK_OK;
 }
 
+static GskVario make_vario(int kind, double range, double sill, double nugget, double gaussian_eps) {
+  GskVario v{};
+  v.kind = kind;
+  v.sill = sill;
+  const double nug = nugget + (kind == GSK_VARIO_GAUSSIAN ? gaussian_eps : 0.0);
+  v.cs = sill - nug;
+  v.range = range;
+  v.inv_r = 1.0 / range;
+  v.inv_r2 = v.inv_r * v.inv_r;
+  v.hcs = 0.5 * v.cs;
+  v.m15cs = -1.5 * v.cs;
+  v.m3ir2 = -3.0 * v.inv_r2;
+  v.m3ir = -3.0 * v.inv_r;
+  return v;
+}
+
 extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) try {
   if (!ctx) return GSK_ERR_INVALID;
   int rc = validate(ctx, p);
@@ -318,18 +335,7 @@ extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) try {
   const int dim = p->dim;
 
   // variogram constants
-  GskVario &v = ctx->vg;
-  v.kind = p->vario_kind;
-  v.sill = p->vario_sill;
-  double nug = p->vario_nugget + (p->vario_kind == GSK_VARIO_GAUSSIAN ? p->gaussian_nugget_eps : 0.0);
-  v.cs = p->vario_sill - nug;
-  v.range = p->vario_range;
-  v.inv_r = 1.0 / p->vario_range;
-  v.inv_r2 = v.inv_r * v.inv_r;
-  v.hcs = 0.5 * v.cs;
-  v.m15cs = -1.5 * v.cs;
-  v.m3ir2 = -3.0 * v.inv_r2;
-  v.m3ir = -3.0 * v.inv_r;
+  ctx->vg = make_vario(p->vario_kind, p->vario_range, p->vario_sill, p->vario_nugget, p->gaussian_nugget_eps);
 
   // estimator
   GskEstimator &es = ctx->es;
@@ -966,6 +972,46 @@ extern "C" GSK_API int gsk_krige(gsk_ctx *ctx, const gsk_problem *p, double *mea
 } catch (const std::exception &e) {
   if (ctx) { cudaStreamSynchronize(ctx->stream2); cudaStreamSynchronize(ctx->stream); }
   return fail(ctx, GSK_ERR_STATE, std::string("gsk_krige: ") + e.what());
+}
+
+// ---------------------------------------------------------------------------------------------
+// LU Gaussian simulation (ref: src/simulation/lu.jl)
+// ---------------------------------------------------------------------------------------------
+extern "C" GSK_API int gsk_lu_plan(gsk_ctx *ctx, int dim, int64_t n_data, int64_t n_sim, const double *const *coords,
+                                   const double *data_values, int vario_kind, double vario_range, double vario_sill,
+                                   double vario_nugget, double gaussian_nugget_eps) try {
+  if (!ctx) return GSK_ERR_INVALID;
+  if (dim < 1 || dim > 3 || n_data < 0 || n_sim < 1 || !coords || (n_data > 0 && !data_values))
+    return fail(ctx, GSK_ERR_INVALID, "gsk_lu_plan: dim in 1..3, n_sim >= 1, coords and (for n_data > 0) data_values required");
+  for (int d = 0; d < dim; ++d)
+    if (!coords[d]) return fail(ctx, GSK_ERR_INVALID, "gsk_lu_plan: coords[d] is NULL for d < dim");
+  if (vario_kind < 0 || vario_kind > 2) return fail(ctx, GSK_ERR_UNSUPPORTED, "unknown variogram kind");
+  if (!(vario_range > 0.0) || !(vario_sill > 0.0) || !(vario_nugget >= 0.0) || !(gaussian_nugget_eps >= 0.0) ||
+      !(vario_sill - vario_nugget - (vario_kind == GSK_VARIO_GAUSSIAN ? gaussian_nugget_eps : 0.0) > 0.0))
+    return fail(ctx, GSK_ERR_INVALID, "range and sill must be > 0, the nugget below the sill");
+  if (n_data + n_sim > 46000) return fail(ctx, GSK_ERR_UNSUPPORTED, "gsk_lu_plan: the dense factor of more than 46 000 points does not fit (lu.jl:60-62: small domains only)");
+  GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  free_plan(ctx);  // the buffers are shared with the Kriging plans
+  ctx->lu_n = 0;
+  const GskVario vg = make_vario(vario_kind, vario_range, vario_sill, vario_nugget, gaussian_nugget_eps);
+  return gsk_lu_plan_impl(ctx, dim, n_data, n_sim, coords, data_values, vg);
+} catch (const std::bad_alloc &) {  // no exception may cross the C ABI
+  return fail(ctx, GSK_ERR_NOMEM, "gsk_lu_plan: out of host memory");
+} catch (const std::exception &e) {
+  return fail(ctx, GSK_ERR_STATE, std::string("gsk_lu_plan: ") + e.what());
+}
+
+extern "C" GSK_API int gsk_lu_sample(gsk_ctx *ctx, const double *w, double *y_out) try {
+  if (!ctx) return GSK_ERR_INVALID;
+  if (ctx->lu_n <= 0) return fail(ctx, GSK_ERR_STATE, "gsk_lu_sample called before gsk_lu_plan");
+  if (!w || !y_out) return fail(ctx, GSK_ERR_INVALID, "gsk_lu_sample: w / y_out are NULL");
+  GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  return gsk_lu_sample_impl(ctx, w, y_out);
+} catch (const std::bad_alloc &) {  // no exception may cross the C ABI
+  return fail(ctx, GSK_ERR_NOMEM, "gsk_lu_sample: out of host memory");
+} catch (const std::exception &e) {
+  return fail(ctx, GSK_ERR_STATE, std::string("gsk_lu_sample: ") + e.what());
 }
 
 extern "C" GSK_API int gsk_measure_fp64_peak(gsk_ctx *ctx, double *dfma_tflops, double *dmma_tflops) {

@@ -12,6 +12,7 @@
 // local kernel uses (local_solve.cuh), from which ν, mean and variance follow:
 //   ν = Gff⁻¹(Gfb − f₀),  mean = Gbz − Gfz·ν,  var = sill − (Gbb − Gfb·ν + f₀·ν)      (SK: μ + Gbz, sill − Gbb)
 #include <math.h>
+#include <string.h>
 
 #include <cmath>
 
@@ -952,5 +953,118 @@ int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, int *d_nn
     if (launches) *launches += 1;
   }
   GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  return GSK_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// LU Gaussian simulation (ref src/simulation/lu.jl:75-160 preprocess, :198-224 lusim): the dense covariance
+// of ALL points — data locations first, then simulation locations — is assembled and factorised once with the same
+// blocked FP64 Cholesky as the global Kriging plan. With C = L Lᵀ, L = [L11 0; A21 L22], the reference's pieces are
+// A21 = (L11⁻¹C12)ᵀ and L22 = chol(C22 − A21 A21ᵀ) (lu.jl:126-133), so one realisation d2 + L22 w2 with d2 = A21 L11⁻¹ z1
+// (lu.jl:132,209) is the lower part of the single triangular product y = L·[L11⁻¹ z1; w2], whose upper part is z1 itself.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+// u = L11⁻¹ z (nd × nd leading block), one CTA: column-oriented forward substitution
+__global__ void __launch_bounds__(256) lu_forward_kernel(const double *__restrict__ A, long long ld, int nd,
+                                                         const double *__restrict__ z, double *__restrict__ u, double *__restrict__ r) {
+  for (int i = threadIdx.x; i < nd; i += 256) r[i] = z[i];
+  __syncthreads();
+  for (int j = 0; j < nd; ++j) {
+    const double uj = r[j] / A[j + (long long)j * ld];
+    __syncthreads();
+    if (threadIdx.x == 0) u[j] = uj;
+    for (int i = j + 1 + threadIdx.x; i < nd; i += 256) r[i] = fma(-A[i + (long long)j * ld], uj, r[i]);
+    __syncthreads();
+  }
+}
+// y[i] = Σ_{j<=i} L[i, j]·v[j]: one warp per row
+__global__ void lu_matvec_kernel(const double *__restrict__ A, long long ld, long long n, const double *__restrict__ v,
+                                 double *__restrict__ y) {
+  const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  double s = 0.0;
+  for (long long j = lane; j <= i; j += 32) s = fma(A[i + j * ld], v[j], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) y[i] = s;
+}
+}  // namespace
+
+int gsk_lu_plan_impl(gsk_ctx *ctx, int dim, long long nd, long long ns, const double *const *coords, const double *z1,
+                     const GskVario &vg) {
+  cudaStream_t st = ctx->stream;
+  const long long n = nd + ns, np = (n + GT - 1) / GT * GT;
+  const int nblk = (int)(np / NB);
+  std::vector<double4> rec((size_t)n);
+  for (long long i = 0; i < n; ++i) {
+    rec[(size_t)i] = make_double4(coords[0][i], dim > 1 ? coords[1][i] : 0.0, dim > 2 ? coords[2][i] : 0.0, 0.0);
+    if (!std::isfinite(rec[(size_t)i].x) || !std::isfinite(rec[(size_t)i].y) || !std::isfinite(rec[(size_t)i].z)) {
+      ctx->err = "point coordinates must be finite";
+      return GSK_ERR_INVALID;
+    }
+  }
+  int rc;
+  double *A = nullptr, *Dinv = nullptr, *vec = nullptr;
+  if ((rc = gsk_buf(ctx, BUF_REC_ORIG, sizeof(double4) * (size_t)n, (void **)&ctx->d_rec_orig)) != GSK_OK) return rc;
+  if ((rc = gsk_buf(ctx, BUF_G_A, sizeof(double) * (size_t)np * np, (void **)&A)) != GSK_OK) return rc;
+  if ((rc = gsk_buf(ctx, BUF_G_DINV, sizeof(double) * (size_t)nblk * NB * NB, (void **)&Dinv)) != GSK_OK) return rc;
+  if ((rc = gsk_buf(ctx, BUF_G_TMP, sizeof(double) * (size_t)(3 * np + 32), (void **)&vec)) != GSK_OK) return rc;
+  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_rec_orig, rec.data(), sizeof(double4) * (size_t)n, cudaMemcpyHostToDevice, st));
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  GArgs ga{ctx->d_rec_orig, n, np, vg, dim};
+  {
+    dim3 grid((unsigned)((np + 255) / 256), (unsigned)np);
+    switch (vg.kind) {
+      case GSK_VARIO_GAUSSIAN: assemble_kernel<GSK_VARIO_GAUSSIAN><<<grid, 256, 0, st>>>(ga, A); break;
+      case GSK_VARIO_SPHERICAL: assemble_kernel<GSK_VARIO_SPHERICAL><<<grid, 256, 0, st>>>(ga, A); break;
+      default: assemble_kernel<GSK_VARIO_EXPONENTIAL><<<grid, 256, 0, st>>>(ga, A); break;
+    }
+  }
+  for (int jb = 0; jb < nblk; ++jb) {
+    const long long j0 = (long long)jb * NB;
+    potrf_diag_kernel<<<1, 256, 0, st>>>(A, np, j0, Dinv + (size_t)jb * NB * NB);
+    const int nrem = nblk - jb - 1;
+    if (nrem > 0) {
+      trsm_panel_kernel<<<nrem, 256, 0, st>>>(A, np, j0, Dinv + (size_t)jb * NB * NB);
+      syrk_kernel<<<(unsigned)((long long)nrem * (nrem + 1) / 2), 256, 0, st>>>(A, np, j0, nrem);
+    }
+  }
+  // v = [L11⁻¹ z1; (w2 filled per realisation)], kept in vec[0:np); vec[np:2np) = y, vec[2np:3np) = scratch
+  GSK_CUDA_CHECK(ctx, cudaMemsetAsync(vec, 0, sizeof(double) * (size_t)(3 * np + 32), st));
+  if (nd > 0) {
+    double *hz = nullptr;
+    if ((rc = gsk_host_stage(ctx, sizeof(double) * (size_t)nd, (void **)&hz)) != GSK_OK) return rc;
+    memcpy(hz, z1, sizeof(double) * (size_t)nd);
+    GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(vec + 2 * np, hz, sizeof(double) * (size_t)nd, cudaMemcpyHostToDevice, st));
+    lu_forward_kernel<<<1, 256, 0, st>>>(A, np, (int)nd, vec + 2 * np, vec, vec + np);
+  }
+  GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  ctx->lu_n = n;
+  ctx->lu_nd = nd;
+  ctx->lu_np = np;
+  ctx->lu_A = A;
+  ctx->lu_vec = vec;
+  return GSK_OK;
+}
+
+int gsk_lu_sample_impl(gsk_ctx *ctx, const double *w, double *y_out) {
+  cudaStream_t st = ctx->stream;
+  const long long n = ctx->lu_n, nd = ctx->lu_nd, np = ctx->lu_np, ns = n - nd;
+  double *vec = ctx->lu_vec;
+  int rc;
+  double *hs = nullptr;
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  if ((rc = gsk_host_stage(ctx, sizeof(double) * (size_t)n, (void **)&hs)) != GSK_OK) return rc;
+  memcpy(hs, w, sizeof(double) * (size_t)ns);
+  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(vec + nd, hs, sizeof(double) * (size_t)ns, cudaMemcpyHostToDevice, st));
+  lu_matvec_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(ctx->lu_A, np, n, vec, vec + np);
+  GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));  // the staging buffer is free again
+  GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(hs, vec + np, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  memcpy(y_out, hs, sizeof(double) * (size_t)n);
   return GSK_OK;
 }

@@ -185,6 +185,10 @@ struct gsk_ctx {
 
   GlobalPlan *gplan = nullptr;
 
+  // LU Gaussian simulation plan (global.cu: gsk_lu_plan_impl): factor of the joint covariance, [L11⁻¹z1; w2] and y
+  long long lu_n = 0, lu_nd = 0, lu_np = 0;
+  double *lu_A = nullptr, *lu_vec = nullptr;
+
   void *bufp[BUF_COUNT] = {};
   size_t bufcap[BUF_COUNT] = {};
   void *h_stage = nullptr;  // pinned host staging buffer
@@ -218,7 +222,10 @@ int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long 
 int gsk_global_plan(gsk_ctx *ctx, const double *hx, const double *hy, const double *hz, const double *hv);
 int gsk_global_execute(gsk_ctx *ctx, long long first, long long count, int *d_nn, int *launches);
 void gsk_global_free(gsk_ctx *ctx);
-int gsk_global_update_values(gsk_ctx *ctx);  // rec_orig carries new values: rebuild E, Y_E, G_EE (L, L⁻¹ stay)
+int gsk_global_update_values(gsk_ctx *ctx);
+int gsk_lu_plan_impl(gsk_ctx *ctx, int dim, long long nd, long long ns, const double *const *coords, const double *z1,
+                     const GskVario &vg);
+int gsk_lu_sample_impl(gsk_ctx *ctx, const double *w, double *y_out);  // rec_orig carries new values: rebuild E, Y_E, G_EE (L, L⁻¹ stay)
 // points.cu
 int gsk_points_sort(gsk_ctx *ctx, long long first, long long count, int **perm, double **sx, double **sy, double **sz);
 int gsk_points_unscatter(gsk_ctx *ctx, const int *perm, long long count, const double *ms, const double *vs,

@@ -717,4 +717,6 @@ def solve(problem: EstimationProblem, solver, ctx: Optional[_abi.Context] = None
     from . import simulation as _sim
     if isinstance(solver, _sim.FFTGS):
         return _sim.solve_fftgs(problem, solver, ctx)
+    if isinstance(solver, _sim.LUGS):
+        return _sim.solve_lugs(problem, solver, ctx)
     raise TypeError(f"solve: unsupported solver {type(solver).__name__}")

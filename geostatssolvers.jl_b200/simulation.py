@@ -188,3 +188,111 @@ def solve_fftgs(problem: SimulationProblem, solver: FFTGS, ctx: Optional[_abi.Co
     pre = preprocess_fftgs(problem, solver, ctx)
     var = problem.variables()[0]
     return [georef({var: solvesingle_fftgs(problem, solver, pre, ctx)}, problem.domain()) for _ in range(problem.nreals())]
+
+
+# --------------------------------------------------------------------------------------------------------------
+# LUGS — LU Gaussian simulation: ref src/simulation/lu.jl
+#   preprocess  lu.jl:75-160   data cells (NearestInit), covariance blocks, Cholesky factors, conditional mean d2
+#   lusim       lu.jl:198-224  y2 = d2 + L22·w2 (second variable: w = ρ·w1 + sqrt(1−ρ²)·w2)
+# The dense factorisation and the matrix–vector product of every realisation run in libgskrige.so (gsk_lu_plan /
+# gsk_lu_sample: the blocked FP64 Cholesky of the global Kriging plan on the JOINT covariance [C11 C12; C21 C22]).
+# --------------------------------------------------------------------------------------------------------------
+_LUGS_DEFAULTS = dict(variogram=None, mean=None, factorization="cholesky")
+
+
+class LUGS:
+    """``LUGS(z=dict(variogram=SphericalVariogram(range=10.0)), rng=2019)`` — parameters: ref lu.jl:66-73. Only the
+    default `factorization=cholesky` exists on the GPU (`lu` is rejected); `correlation` couples two variables."""
+
+    def __init__(self, *pairs, rng=None, correlation=0.0, **kwpairs):
+        self.vparams = {}
+        for item in list(pairs) + list(kwpairs.items()):
+            for var, params in (list(item.items()) if isinstance(item, dict) else [item]):
+                unknown = set(params) - set(_LUGS_DEFAULTS)
+                if unknown:
+                    raise TypeError(f"unknown LUGS parameter(s) {sorted(unknown)} for variable {var}")
+                self.vparams[var] = dict(params)
+        self.correlation = float(correlation)
+        self.rng = rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
+
+    def params(self, var):
+        p = dict(_LUGS_DEFAULTS)
+        p.update(self.vparams.get(var, {}))
+        if p["variogram"] is None:
+            p["variogram"] = GaussianVariogram()
+        if p["factorization"] not in ("cholesky", None):
+            raise _unsupported("LUGS `factorization` other than cholesky")
+        return p
+
+
+def _nearest_cells(pdomain, coords):
+    """NearestInit (GeoStatsBase initbuff): every datum goes to the domain element nearest to it; a later datum
+    overwrites an earlier one in the same element. Returns (cells in first-seen order, index of the datum kept)."""
+    cents = pdomain.centroids()
+    n = coords[0].shape[0]
+    if isinstance(pdomain, CartesianGrid):
+        dims = pdomain.dims
+        ijk = [np.clip(np.floor((coords[a] - pdomain.origin[a]) / pdomain.spacing[a]).astype(np.int64), 0, dims[a] - 1)
+               for a in range(len(dims))]
+        lin = np.zeros(n, dtype=np.int64)
+        for a in reversed(range(len(dims))):
+            lin = lin * dims[a] + ijk[a]
+    else:
+        P = np.stack(cents, 1)
+        lin = np.array([int(np.argmin(((P - np.array([c[i] for c in coords])) ** 2).sum(1))) for i in range(n)], dtype=np.int64)
+    keep = {}
+    for i, c in enumerate(lin.tolist()):
+        keep[c] = i
+    cells = np.array(sorted(keep), dtype=np.int64)               # findall(mask): ascending element index (lu.jl:113)
+    return cells, np.array([keep[c] for c in cells.tolist()], dtype=np.int64)
+
+
+def preprocess_lugs(problem: SimulationProblem, solver: LUGS, var: str, ctx: _abi.Context) -> dict:
+    """ref lu.jl:75-160 for one variable: the joint covariance is factorised on the GPU and stays resident in `ctx`"""
+    pdomain = problem.domain()
+    p = solver.params(var)
+    gamma = p["variogram"]
+    if not isinstance(gamma, _Variogram) or gamma.kind < 0:
+        raise _unsupported(f"variogram {type(gamma).__name__}")
+    cents = pdomain.centroids()
+    npts = pdomain.nelements()
+    pdata = problem.data()
+    if pdata is not None and var in pdata.table:
+        dcoords = pdata.domain.centroids()
+        dlocs, kept = _nearest_cells(pdomain, dcoords)
+        z1 = np.asarray(pdata.table[var], dtype=np.float64)[kept]
+    else:
+        dlocs, z1 = np.zeros(0, dtype=np.int64), np.zeros(0)
+    mask = np.ones(npts, dtype=bool)
+    mask[dlocs] = False
+    slocs = np.flatnonzero(mask)                                  # lu.jl:117
+    order = np.concatenate([dlocs, slocs])
+    ctx.lu_plan([c[order] for c in cents], len(dlocs), z1, vario_kind=gamma.kind, vario_range=gamma.range,
+                vario_sill=gamma.sill, vario_nugget=gamma.nugget)
+    if p["mean"] is not None and len(dlocs) > 0:
+        import warnings
+        warnings.warn("mean can only be specified in unconditional simulation")   # lu.jl:137-139
+    mu = 0.0 if p["mean"] is None else float(p["mean"])
+    return dict(dlocs=dlocs, slocs=slocs, z1=z1, mu=mu, npts=npts)
+
+
+def lusim(ctx: _abi.Context, pre: dict, w2: np.ndarray, rho=None, w1=None) -> np.ndarray:
+    """ref lu.jl:198-224 for the draws w2 (and, for the second of two correlated variables, ρ and the first's draws)"""
+    w = w2 if rho is None else rho * w1 + np.sqrt(1.0 - rho ** 2) * w2
+    joint = ctx.lu_sample(w)                                       # [z1; d2 + L22·w]
+    nd = len(pre["dlocs"])
+    y = np.empty(pre["npts"])
+    y[pre["dlocs"]] = joint[:nd]
+    y[pre["slocs"]] = joint[nd:]
+    if nd == 0:
+        y += pre["mu"]                                             # lu.jl:221
+    return y
+
+
+def solve_lugs(problem: SimulationProblem, solver: LUGS, ctx: Optional[_abi.Context] = None):
+    """``solve(problem, LUGS(...))`` for one variable — a list of `nreals` GeoTables."""
+    ctx = ctx or default_context()
+    var = problem.variables()[0]
+    pre = preprocess_lugs(problem, solver, var, ctx)
+    ns = len(pre["slocs"])
+    return [georef({var: lusim(ctx, pre, solver.rng.standard_normal(ns))}, problem.domain()) for _ in range(problem.nreals())]

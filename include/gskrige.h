@@ -212,6 +212,18 @@ GSK_API int gsk_get_timing(const gsk_ctx *ctx, gsk_timing *out);
  * so that gsk_timing.ms_search / ms_solve are filled; off by default (no synchronisation in gsk_execute) */
 GSK_API int gsk_set_phase_timing(gsk_ctx *ctx, int on);
 
+/* ---- LU Gaussian simulation: replaces the dense factorisation of preprocess (ref: src/simulation/lu.jl:118-139) and
+ *      lusim (lu.jl:198-224) -------------------------------------------------------------------------------------
+ * coords[d] hold n_data + n_sim points, the DATA locations first (their values in data_values), then the simulation
+ * locations. The joint covariance sill − γ(h) is assembled and factorised on the GPU (blocked FP64 Cholesky, the same
+ * kernels as the global Kriging plan) and stays resident. */
+GSK_API int gsk_lu_plan(gsk_ctx *ctx, int dim, int64_t n_data, int64_t n_sim, const double *const *coords,
+                        const double *data_values, int vario_kind, double vario_range, double vario_sill,
+                        double vario_nugget, double gaussian_nugget_eps);
+/* one realisation: w = n_sim standard normal draws (the caller's RNG; for two correlated variables the caller passes
+ * ρ·w₁ + √(1−ρ²)·w₂, lu.jl:213). y_out (n_data + n_sim): the data values, then d₂ + L₂₂·w (lu.jl:209-219) */
+GSK_API int gsk_lu_sample(gsk_ctx *ctx, const double *w, double *y_out);
+
 /* ---- host helpers shared by every binding ------------------------------------------ */
 /* number of targets of the problem's domain (grid product or n_points) */
 GSK_API int64_t gsk_num_targets(const gsk_problem *prob);

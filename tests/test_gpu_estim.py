@@ -274,3 +274,54 @@ def test_fftgs_conditional_simulation(gsk, oracle, maxneighbors):
     for s in sols:
         z = np.asarray(s.z)
         assert abs(np.sum(z * z) / (z.size - 1) - 1.0) < 1e-9
+
+
+# ---- LU Gaussian simulation (ref src/simulation/lu.jl): dense joint factor + one triangular product per realisation ----
+@pytest.mark.parametrize("conditional", [False, True])
+def test_lugs_vs_numpy_cholesky(gsk, conditional):
+    """lu.jl:118-133 (C11, C12, C22, L11, B12, d2, L22) and lusim (lu.jl:198-224) restated with numpy's Cholesky"""
+    from gskrige.simulation import variogram_values, preprocess_lugs, lusim
+    grid = gsk.CartesianGrid(24, 20)
+    gamma = gsk.SphericalVariogram(range=9.0, sill=1.3, nugget=0.1)
+    rng = np.random.default_rng(4)
+    if conditional:
+        dcoords = [np.array([3.2, 10.7, 20.1, 3.4, 15.5]), np.array([2.2, 11.3, 17.9, 2.6, 5.5])]   # data 0 and 3 share a cell
+        dvals = np.array([0.8, -0.4, 1.1, 0.6, -1.2])
+        problem = gsk.SimulationProblem(gsk.georef({"z": dvals}, np.stack(dcoords, 0)), grid, "z", 2)
+    else:
+        problem = gsk.SimulationProblem(grid, "z", 2)
+    solver = gsk.LUGS(z=dict(variogram=gamma, mean=None if conditional else 2.5), rng=9)
+    with gsk.Context(0) as c:
+        pre = preprocess_lugs(problem, solver, "z", c)
+        dlocs, slocs = pre["dlocs"], pre["slocs"]
+        cents = np.stack(grid.centroids(), 1)
+        cov = lambda A, B: gamma.sill - variogram_values(gamma, np.sqrt(((A[:, None, :] - B[None, :, :]) ** 2).sum(-1)))
+        S = cents[slocs]
+        C22 = cov(S, S)
+        if conditional:
+            assert len(dlocs) == 4 and pre["z1"].tolist() == [0.6, -1.2, -0.4, 1.1]       # the later datum wins its cell
+            D = cents[dlocs]
+            L11 = np.linalg.cholesky(cov(D, D))
+            B12 = np.linalg.solve(L11, cov(D, S))
+            d2 = B12.T @ np.linalg.solve(L11, pre["z1"])
+            L22 = np.linalg.cholesky(C22 - B12.T @ B12)
+        else:
+            d2, L22 = 0.0, np.linalg.cholesky(C22)
+        for _ in range(2):
+            w = rng.standard_normal(len(slocs))
+            y = lusim(c, pre, w)
+            want = np.empty(grid.nelements())
+            want[dlocs] = pre["z1"]
+            want[slocs] = d2 + L22 @ w
+            if not conditional:
+                want += 2.5
+            np.testing.assert_allclose(y, want, rtol=1e-9, atol=1e-10)
+        w1, w2 = rng.standard_normal(len(slocs)), rng.standard_normal(len(slocs))
+        y2 = lusim(c, pre, w2, rho=0.6, w1=w1)                                             # lu.jl:213
+        np.testing.assert_allclose(y2[slocs] - (2.5 if not conditional else 0.0), d2 + L22 @ (0.6 * w1 + 0.8 * w2), rtol=1e-9, atol=1e-10)
+        with pytest.raises(gsk.GskError):
+            c.plan(gsk.synth.config_spec("C2", scale=0.05)) or c.lu_sample(w)               # a Kriging plan replaces the LU plan
+        sols = gsk.solve(problem, solver, ctx=c)
+        assert len(sols) == 2 and np.asarray(sols[0].z).shape == (480,)
+    with pytest.raises(gsk.UnsupportedOption):
+        gsk.LUGS(z=dict(factorization="lu")).params("z")
