@@ -319,6 +319,18 @@ __device__ __forceinline__ void gsk_store_result(const GskOut &o, long long t, d
   }
 }
 
+// one field of one target (field 0: mean, 1: variance) — for kernels that stage a CTA's results in shared memory and
+// write them with consecutive threads (coalesced 8-byte stores: thread i → target t0 + i)
+__device__ __forceinline__ void gsk_store_field(const GskOut &o, int field, long long t, double x) {
+  if (o.multicast) {
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"((field ? o.var[0] : o.mean[0]) + t), "d"(x) : "memory");
+    return;
+  }
+#pragma unroll
+  for (int p = 0; p < GSK_MAX_PEERS; ++p)
+    if (p < o.n) (field ? o.var[p] : o.mean[p])[t] = x;
+}
+
 __device__ __forceinline__ double gsk_ipow(double x, int e) {
   const double x1 = (e >= 1) ? x : 1.0;
   return (e >= 2) ? x1 * x : x1;

@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const
     for (int i = tid; i < 3 * a.nsup; i += NTH) sup[i] = UNIT ? a.sup[i] * cscale : a.sup[i];
   __syncthreads();
 
-  double *S = sm + nsup_pad + (size_t)grp * SK_GSZ;
+  double *res = sm + nsup_pad;                      // [2][TPC]: the CTA's results, staged for coalesced stores
+  double *S = sm + nsup_pad + 2 * TPC + (size_t)grp * SK_GSZ;
   double *Sl = S + l;
   const GskVario vg = a.vg;
 
@@ -284,7 +285,15 @@ __global__ void __launch_bounds__(NTH, 512 / NTH) local_solve_small_kernel(const
       if (a.flags & GSK_FLAG_CLAMP_VARIANCE) var = (var > 0.0 || var != var) ? var : 0.0;
       if (a.flags & GSK_FLAG_SQRT_ROUNDTRIP) { double sd = sqrt(var); var = sd * sd; }
     }
-    gsk_store_result(a.out, t, mean, var);
+    res[grp] = mean;
+    res[TPC + grp] = var;
+  }
+  // coalesced result stores: thread i writes the mean of the CTA's i-th target, thread TPC + i its variance
+  __syncthreads();
+  if (tid < 2 * TPC) {
+    const int i = tid % TPC, field = tid / TPC;
+    const long long ti = (long long)blockIdx.x * TPC + i;
+    if (ti < a.count) gsk_store_field(a.out, field, ti, res[tid]);
   }
 }
 
@@ -294,7 +303,7 @@ inline cudaError_t launch_small_full(const GskLocalArgs &a, cudaStream_t st) {
   GskLocalArgs b = a;
   b.sup_smem = (a.nsup <= GSK_MAX_SUPPORT) ? 1 : 0;
   const int nsup_pad = b.sup_smem ? ((3 * a.nsup + 3) & ~3) : 0;
-  const size_t smem = sizeof(double) * ((size_t)nsup_pad + (NTH / 4) * (size_t)SK_GSZ);
+  const size_t smem = sizeof(double) * ((size_t)nsup_pad + 2 * (NTH / 4) + (NTH / 4) * (size_t)SK_GSZ);
   auto kern = local_solve_small_kernel<DIM, VK, FULL, NUG0, NTH>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return err;

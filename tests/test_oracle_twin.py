@@ -55,3 +55,29 @@ def test_uk_exponents_order(gsk, oracle):
         for dim in (1, 2, 3):
             assert oracle.uk_exponents(deg, dim).tolist() == TW.uk_exponents(deg, dim).tolist()
             assert gsk.uk_exponents(deg, dim).tolist() == TW.uk_exponents(deg, dim).tolist()
+
+
+def test_gaussian_global_tolerance_floor_is_entry_rounding(gsk):
+    """Why the Gaussian global config (C1) is compared with an absolute floor of 2e-8 instead of a bare rtol 1e-9:
+    rounding the covariance ENTRIES differently by one ulp (the device's exp vs glibc's) already moves the kriging
+    mean by ~2e-9 — cond(C) ≈ 5.6e7, dual weights up to 6e4 — whatever the solver. (Measured GPU − oracle on C1:
+    1.9e-9 with the mean taken from dual weights refined in double-double arithmetic, 2.3e-9 before.)"""
+    import numpy_twin as TW
+    spec = gsk.synth.config_spec("C1")
+    X, z = np.stack(spec.coords, 1), spec.values
+    n = len(z)
+    d = np.sqrt(((X[:, None, :] - X[None, :, :]) ** 2).sum(-1))
+    C = 1.0 - TW.variogram(TW.GAUSSIAN, d, 35.0, 1.0, 0.0)
+    K = np.zeros((n + 1, n + 1)); K[:n, :n] = C; K[:n, n] = 1.0; K[n, :n] = 1.0
+    rhs = np.zeros(n + 1); rhs[:n] = z
+    rng = np.random.default_rng(0)
+    E = np.triu(rng.choice([-1.0, 0.0, 1.0], size=(n, n)), 1)
+    Kp = K.copy(); Kp[:n, :n] = C * (1.0 + (E + E.T) * 2.2e-16)
+    w, wp = np.linalg.solve(K, rhs), np.linalg.solve(Kp, rhs)
+    ctr = np.stack(spec.target_centers(), 1)[::37]
+    B = np.zeros((n + 1, len(ctr)))
+    for s in np.stack(spec.support, 1):
+        B[:n] += 1.0 - TW.variogram(TW.GAUSSIAN, np.sqrt((((ctr + s)[None, :, :] - X[:, None, :]) ** 2).sum(-1)), 35.0, 1.0, 0.0)
+    B[:n] /= len(spec.support[0]); B[n] = 1.0
+    moved = np.abs(w @ B - wp @ B).max()
+    assert 2e-10 < moved < 2e-8
