@@ -253,6 +253,8 @@ def load_library(path: os.PathLike | None = None):
     lib.gsk_krige.restype = C.c_int
     lib.gsk_krige_multi.argtypes = [_ip, C.c_int, pp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
     lib.gsk_krige_multi.restype = C.c_int
+    lib.gsk_krige_multi_release.argtypes = []
+    lib.gsk_krige_multi_release.restype = None
     lib.gsk_plan.argtypes = [ctx, pp]
     lib.gsk_plan.restype = C.c_int
     lib.gsk_execute.argtypes = [ctx, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -287,7 +289,7 @@ def load_library(path: os.PathLike | None = None):
 
 
 EXPORTED_SYMBOLS = [
-    "gsk_create", "gsk_destroy", "gsk_last_error", "gsk_set_stream", "gsk_synchronize", "gsk_krige", "gsk_krige_multi", "gsk_plan",
+    "gsk_create", "gsk_destroy", "gsk_last_error", "gsk_set_stream", "gsk_synchronize", "gsk_krige", "gsk_krige_multi", "gsk_krige_multi_release", "gsk_plan",
     "gsk_execute", "gsk_execute_peers", "gsk_update_values", "gsk_lu_plan", "gsk_lu_sample", "gsk_get_timing", "gsk_set_phase_timing", "gsk_num_targets", "gsk_uk_exponents", "gsk_default_support",
     "gsk_measure_fp64_peak", "gsk_abi_version",
 ]

@@ -1028,6 +1028,16 @@ std::mutex g_multi_mutex;
 std::vector<gsk_ctx *> g_multi_ctx;   // slot i serves piece i (re-created if the device id changes)
 }  // namespace
 
+// destroys the contexts gsk_krige_multi keeps between calls (device buffers, streams); the next call re-creates them
+extern "C" GSK_API void gsk_krige_multi_release(void) {
+  std::lock_guard<std::mutex> lock(g_multi_mutex);
+  for (gsk_ctx *&c : g_multi_ctx) {
+    if (c) gsk_destroy(c);
+    c = nullptr;
+  }
+  g_multi_ctx.clear();
+}
+
 extern "C" GSK_API int gsk_krige_multi(const int *device_ids, int n_devices, const gsk_problem *p, double *mean_out,
                                        double *var_out, int32_t *nneigh_out, int32_t *neigh_idx_out, char *errbuf,
                                        int errbuf_len) try {

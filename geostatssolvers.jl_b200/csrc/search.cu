@@ -23,7 +23,7 @@
 namespace {
 
 constexpr int NT = 128;       // targets (threads) per CTA
-constexpr int CB = 2;         // candidates whose loads and distances are issued together
+constexpr int CB = 4;         // candidates whose loads and distances are issued together
 constexpr int SCAP_MAX = 1024;  // upper bound of staged records per chunk (32 KB)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

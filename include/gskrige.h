@@ -185,6 +185,10 @@ GSK_API int gsk_krige_multi(const int *device_ids, int n_devices, const gsk_prob
                             double *var_out, int32_t *nneigh_out, int32_t *neigh_idx_out, char *errbuf,
                             int errbuf_len);
 
+/* The per-device contexts of gsk_krige_multi (buffers, streams) are cached in the process between calls — one call at a
+ * time per process; gsk_krige_multi_release destroys them (call it before unloading the library or to give the memory back). */
+GSK_API void gsk_krige_multi_release(void);
+
 /* ---- resident two-step form: replaces preprocess' searcher/estimator construction
  *      (krig.jl:110,117; fit at krig.jl:176) and then the per-target loops ------------- */
 /* uploads samples, builds the bin structure (local) or assembles + factorises the

@@ -418,6 +418,9 @@ def test_krige_multi_single_process(gsk, ctx):
         assert np.array_equal(part[0], ref[0][100:877])
     with pytest.raises(gsk.GskError):
         gsk.krige_multi(spec, [99])
+    gsk.load_library().gsk_krige_multi_release()          # the cached per-device contexts are given back …
+    again = gsk.krige_multi(spec, [0, 0])                 # … and re-created on demand
+    assert np.array_equal(again[0], ref[0])
 
 
 def test_plain_c_host_end_to_end(gsk, oracle, tmp_path):
@@ -495,3 +498,24 @@ def test_config_c4_full_size_golden(gsk, ctx):
     # (values of order 1): rtol 1e-9 with that absolute floor (north_star's tolerance, floor stated per SURVEY §8d)
     np.testing.assert_allclose(mean, g["mean"], rtol=1e-9, atol=2e-9)
     np.testing.assert_allclose(var, g["var"], rtol=1e-9, atol=2e-9)
+
+
+@pytest.mark.parametrize("name", ["C2", "C3a", "C3b", "C5"])
+def test_local_configs_full_size_golden(gsk, ctx, name):
+    """The local BASELINE configs at their FULL sample counts against 1 024 golden targets each from the independent
+    numpy + LAPACK restatement (tests/golden/make_golden_local.py: brute-force k-NN, dsytrf / dpotrf): neighbour
+    lists bit-exact, mean and variance rtol 1e-9 (absolute floor 1e-12·scale for values that cross zero)."""
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / "local_full_1024.npz")
+    spec = gsk.synth.config_spec(name)
+    chosen = g[f"{name}/targets"]
+    # the chosen cells as an explicit point list (their centroids, formed exactly as the library forms them) with the
+    # grid's block support — the same targets without a 134M-entry traversal order for C5
+    lin, pts = chosen.copy(), []
+    for d in range(spec.dim):
+        pts.append(spec.grid_origin[d] + ((lin % spec.grid_dims[d]).astype(np.float64) + 0.5) * spec.grid_spacing[d])
+        lin //= spec.grid_dims[d]
+    sp = gsk.ProblemSpec(coords=spec.coords, values=spec.values, points=pts, support=spec.support, **spec.params)
+    mean, var, nn, idx = ctx.krige(sp, want_neighbors=True)
+    assert np.array_equal(idx, g[f"{name}/idx"])
+    assert_parity(mean, var, g[f"{name}/mean"], g[f"{name}/var"], scale=max(1.0, np.abs(spec.values).max()))
