@@ -434,7 +434,7 @@ extern "C" GSK_API int gsk_plan(gsk_ctx *ctx, const gsk_problem *p) try {
       const int q = p->n_support;
       int want = 1;
       for (int d = 0; d < dim; ++d) want *= 3;
-      bool ok = (q == want);
+      bool ok = (q == want) && dim >= 2;  // (1-D problems run the 2-D kernels with y = 0: their 3 offsets are not a 3×3 grid)
       for (int d = 0; d < 3 && ok; ++d) {
         const int stride = (d == 0) ? 1 : (d == 1 ? 3 : 9);
         for (int a = 0; a < 3; ++a) ctx->sup_ax[d][a] = (d < dim) ? sup[(size_t)d * q + (size_t)a * stride] : 0.0;

@@ -519,3 +519,24 @@ def test_local_configs_full_size_golden(gsk, ctx, name):
     mean, var, nn, idx = ctx.krige(sp, want_neighbors=True)
     assert np.array_equal(idx, g[f"{name}/idx"])
     assert_parity(mean, var, g[f"{name}/mean"], g[f"{name}/var"], scale=max(1.0, np.abs(spec.values).max()))
+
+
+# ---- the block-pool solve kernel (20 < k <= 64, at most 6 drift terms): both shapes, every model ----
+@pytest.mark.parametrize("k", [21, 24, 31, 32, 33, 40, 57, 64])
+@pytest.mark.parametrize("vk,nugget", [(0, 0.0), (1, 0.0), (1, 0.07), (2, 0.0), (2, 0.07)])
+@pytest.mark.parametrize("dim,est,deg", [(3, 0, 0), (3, 1, 0), (3, 2, 1), (2, 1, 0), (2, 2, 1), (2, 2, 2), (1, 1, 0)])
+def test_block_pool_matrix(gsk, ctx, oracle, k, vk, nugget, dim, est, deg):
+    """k = 21 … 32 runs two targets per warp (4 neighbour blocks), k = 33 … 64 one warp per target (8 blocks); partial last
+    blocks (k not a multiple of 8), no-nugget and nugget variants (the d² == 0 select), SK / OK / UK (up to 6 drift
+    terms: UK degree 2 in 2-D), a ball that leaves some targets with fewer than k neighbours, 1-D to 3-D."""
+    grid = {1: (160,), 2: (17, 13), 3: (8, 7, 6)}[dim]
+    n = {1: 90, 2: 260, 3: 420}[dim]
+    coords, vals = gsk.synth.make_samples(300 + dim, n, grid, seed_extra=k + 7 * vk + est)
+    rng_ = {1: 50.0, 2: 11.0, 3: 7.0}[dim]
+    radius = {1: 38.0, 2: 5.5, 3: 3.9}[dim] if (k % 8 == 0) else None     # roughly the k-NN radius: some targets get fewer
+    spec = gsk.ProblemSpec(coords=coords, values=vals, grid_dims=grid, support=gsk.default_support_py([1.0] * dim, rng_),
+                           vario_kind=vk, vario_range=rng_, vario_sill=1.2, vario_nugget=nugget, estimator=est,
+                           uk_degree=deg, sk_mean=float(vals.mean()), max_neighbors=min(k, n), min_neighbors=3,
+                           ball_radius=float("nan") if radius is None else radius)
+    loose = vk == 0 or deg == 2 or (est == 2 and k >= 40)   # Gaussian / drift monomials in raw coordinates: cond ≳ 1e6
+    _check(gsk, ctx, oracle, spec, **(dict(atol_mean=2e-7, atol_var=2e-7) if loose else {}))
