@@ -72,16 +72,14 @@ __host__ inline Layout make_layout(int k, int e) {
   return L;
 }
 
-// 1/sqrt(d) to ~1 ulp: MUFU.RSQ64H seed (2^-22) + two Newton steps
+// 1/sqrt(d) to ~1 ulp: MUFU.RSQ64H seed (2^-22) + one cubically convergent step, 1/sqrt(d) = y(1 + e/2 + 3e²/8 + O(e³))
+// with e = 1 − d·y² — a dependent chain of four FP64 operations (two Newton steps are six; the pivot of every panel
+// column waits for this value)
 __device__ __forceinline__ double gsk_rsqrt(double d) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-  const double h = 0.5 * d;
-  double r = fma(-(h * y), y, 0.5);
-  y = fma(y, r, y);
-  r = fma(-(h * y), y, 0.5);
-  y = fma(y, r, y);
-  return y;
+  const double e = fma(-(d * y), y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
 }
 
 // sqrt(u) for u > 0 (u == 0 yields NaN, discarded by the callers' d2 > 0 select)
