@@ -929,7 +929,6 @@ extern "C" GSK_API int gsk_krige(gsk_ctx *ctx, const gsk_problem *p, double *mea
   if (!ctx) return GSK_ERR_INVALID;
   if (!mean_out || !var_out) return fail(ctx, GSK_ERR_INVALID, "mean_out / var_out are NULL");
   int rc = GSK_OK;
-  bool planned_here = true;
   if (p && (p->flags & GSK_FLAG_REUSE_PLAN) && p->abi_version == GSK_ABI_VERSION) {
     // same problem as the resident plan? then nothing is uploaded or rebuilt; same problem with other VALUES (the
     // conditional-simulation callers, fft.jl:184-188)? then only the values go up and bins / neighbour lists /
@@ -947,7 +946,6 @@ extern "C" GSK_API int gsk_krige(gsk_ctx *ctx, const gsk_problem *p, double *mea
         ctx->nbr_reuse = true;
       }
       ctx->timing.ms_plan = 0.0;
-      planned_here = false;
     } else {
       rc = gsk_plan(ctx, p);
       if (rc != GSK_OK) return rc;
@@ -960,7 +958,6 @@ extern "C" GSK_API int gsk_krige(gsk_ctx *ctx, const gsk_problem *p, double *mea
     rc = gsk_plan(ctx, p);
     if (rc != GSK_OK) return rc;
   }
-  (void)planned_here;
   const int64_t T = ctx->n_targets;
   const int64_t first = p->target_first;
   const int64_t count = p->target_count < 0 ? T - first : p->target_count;

@@ -36,6 +36,10 @@ int gsk_launch_local_solve(gsk_ctx *ctx, cudaStream_t st, long long first, long 
     a.out.mean[p] += out_off;
     a.out.var[p] += out_off;
   }
+  // Which kernel: k <= 20 with Simple / Ordinary Kriging → the small kernel (4 lanes per target, everything static);
+  // 20 < k <= 64 with at most 6 drift terms → the block-pool kernels (local_solve_wpt.cuh: two targets per warp up to
+  // k = 32, one warp per target above); everything else (Universal Kriging with k <= 20, more than 6 drift terms,
+  // 64 < k <= 96) → the column-packed kernel in the smallest configuration that holds k + extra rows.
   // extra rows: b, z, then the c drift rows
   const int e = 2 + ctx->es.nterms;
   auto rows = [&](int W) { return (a.k + W - 1) / W * W + (e + W - 1) / W * W; };
