@@ -19,7 +19,7 @@ from .host import (CartesianGrid, EstimationProblem, Euclidean, ExponentialVario
                    default_context, degC, elunit, embeddim, exactsolve, georef, kriging_ui, maxneighbors, nelements,
                    preprocess, searcher_ui, solve, traverse, uadjust)
 from . import sharding, simulation, synth  # noqa: F401
-from .simulation import FFTGS, LUGS, SimulationProblem  # noqa: F401
+from .simulation import FFTGS, LUGS, SGS, SimulationProblem  # noqa: F401
 from .sharding import gather_slabs, slab_bounds  # noqa: F401
 
 __version__ = "0.1.0"

@@ -269,6 +269,13 @@ def load_library(path: os.PathLike | None = None):
     lib.gsk_lu_plan.restype = C.c_int
     lib.gsk_lu_sample.argtypes = [ctx, _dp, _dp]
     lib.gsk_lu_sample.restype = C.c_int
+    lib.gsk_sgs_plan.argtypes = ([ctx, C.c_int, C.c_int64, C.POINTER(_dp), C.POINTER(C.c_int64), C.c_int] + [C.c_double] * 5
+                                 + [C.c_int, C.c_int, C.c_double])
+    lib.gsk_sgs_plan.restype = C.c_int
+    lib.gsk_sgs_sample.argtypes = [ctx, C.c_int, _dp, _dp, _dp]
+    lib.gsk_sgs_sample.restype = C.c_int
+    lib.gsk_sgs_weights.argtypes = [ctx, _ip, _ip, _dp, _dp]
+    lib.gsk_sgs_weights.restype = C.c_int
     lib.gsk_get_timing.argtypes = [ctx, C.POINTER(GskTiming)]
     lib.gsk_get_timing.restype = C.c_int
     lib.gsk_set_phase_timing.argtypes = [ctx, C.c_int]
@@ -290,7 +297,7 @@ def load_library(path: os.PathLike | None = None):
 
 EXPORTED_SYMBOLS = [
     "gsk_create", "gsk_destroy", "gsk_last_error", "gsk_set_stream", "gsk_synchronize", "gsk_krige", "gsk_krige_multi", "gsk_krige_multi_release", "gsk_plan",
-    "gsk_execute", "gsk_execute_peers", "gsk_update_values", "gsk_lu_plan", "gsk_lu_sample", "gsk_get_timing", "gsk_set_phase_timing", "gsk_num_targets", "gsk_uk_exponents", "gsk_default_support",
+    "gsk_execute", "gsk_execute_peers", "gsk_update_values", "gsk_lu_plan", "gsk_lu_sample", "gsk_sgs_plan", "gsk_sgs_sample", "gsk_sgs_weights", "gsk_get_timing", "gsk_set_phase_timing", "gsk_num_targets", "gsk_uk_exponents", "gsk_default_support",
     "gsk_measure_fp64_peak", "gsk_abi_version",
 ]
 
@@ -381,6 +388,48 @@ class Context:
         y = np.empty(self._lu_n, dtype=np.float64)
         self._check(self.lib.gsk_lu_sample(self._h, _ptr(w), _ptr(y)))
         return y
+
+    # -- sequential Gaussian simulation ------------------------------------------------
+    def sgs_plan(self, coords, rank, *, vario_kind, vario_range, vario_sill=1.0, vario_nugget=0.0, gaussian_nugget_eps=1e-6,
+                 mean=0.0, min_neighbors=1, max_neighbors=10, ball_radius=float("nan")):
+        """coords: dim arrays with the n centroids of the domain; rank[i] = -1 where element i holds data, else its
+        position in the simulation path among the other elements (``gsk_sgs_plan``)."""
+        cs = [_as_f64(c) for c in coords]
+        n = cs[0].shape[0]
+        arr = (_dp * 3)(*[_ptr(cs[d]) if d < len(cs) else None for d in range(3)])
+        rk = np.ascontiguousarray(rank, dtype=np.int64)
+        if rk.shape != (n,):
+            raise ValueError("rank must have one entry per element")
+        self._sgs_n, self._sgs_k = n, min(int(max_neighbors), n)
+        self._check(self.lib.gsk_sgs_plan(self._h, len(cs), n, arr, rk.ctypes.data_as(C.POINTER(C.c_int64)), int(vario_kind),
+                                          float(vario_range), float(vario_sill), float(vario_nugget),
+                                          float(gaussian_nugget_eps), float(mean), int(min_neighbors), int(max_neighbors),
+                                          float(ball_radius)))
+
+    def sgs_sample(self, z, values=None):
+        """z: (nreal, n) or (n,) standard normal draws per element; values: (n,) read where rank < 0. Returns the
+        realisations with the shape of z (``gsk_sgs_sample``)."""
+        z = _as_f64(z)
+        n = self._sgs_n
+        if z.shape[-1] != n or z.ndim > 2:
+            raise ValueError("z must be (n,) or (nreal, n)")
+        nreal = 1 if z.ndim == 1 else z.shape[0]
+        v = _as_f64(values) if values is not None else None
+        if v is not None and v.shape != (n,):
+            raise ValueError("values must have one entry per element")
+        out = np.empty_like(z)
+        self._check(self.lib.gsk_sgs_sample(self._h, nreal, _ptr(v) if v is not None else None, _ptr(z), _ptr(out)))
+        return out
+
+    def sgs_weights(self):
+        """(nneigh, idx, weights, sigma) of the resident plan (``gsk_sgs_weights``)."""
+        n, k = self._sgs_n, self._sgs_k
+        nn = np.empty(n, dtype=np.int32)
+        idx = np.empty((n, k), dtype=np.int32)
+        lam = np.empty((n, k))
+        sig = np.empty(n)
+        self._check(self.lib.gsk_sgs_weights(self._h, nn.ctypes.data_as(_ip), idx.ctypes.data_as(_ip), _ptr(lam), _ptr(sig)))
+        return nn, idx, lam, sig
 
     def execute(self, first, count, d_mean, d_var, d_nneigh=0, d_idx=0):
         """Device pointers (ints). Asynchronous on the context stream."""

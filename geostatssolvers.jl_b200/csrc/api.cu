@@ -181,6 +181,7 @@ static void free_plan(gsk_ctx *ctx) {
   ctx->d_sup = nullptr;
   for (int d = 0; d < 3; ++d) ctx->d_pts[d] = nullptr;
   gsk_global_free(ctx);
+  gsk_sgs_free(ctx);
   ctx->planned = false;
   ctx->nbr_cached = false;
   ctx->nbr_reuse = false;
@@ -1009,6 +1010,66 @@ extern "C" GSK_API int gsk_lu_sample(gsk_ctx *ctx, const double *w, double *y_ou
   return fail(ctx, GSK_ERR_NOMEM, "gsk_lu_sample: out of host memory");
 } catch (const std::exception &e) {
   return fail(ctx, GSK_ERR_STATE, std::string("gsk_lu_sample: ") + e.what());
+}
+
+#define GSK_SGS_MAX_NEIGHBORS 64
+extern "C" GSK_API int gsk_sgs_plan(gsk_ctx *ctx, int dim, int64_t n, const double *const *coords, const int64_t *rank,
+                                    int vario_kind, double vario_range, double vario_sill, double vario_nugget,
+                                    double gaussian_nugget_eps, double mean, int min_neighbors, int max_neighbors,
+                                    double ball_radius) try {
+  if (!ctx) return GSK_ERR_INVALID;
+  if (dim < 1 || dim > 3 || n < 1 || !coords || !rank)
+    return fail(ctx, GSK_ERR_INVALID, "gsk_sgs_plan: dim in 1..3, n >= 1, coords and rank required");
+  for (int d = 0; d < dim; ++d)
+    if (!coords[d]) return fail(ctx, GSK_ERR_INVALID, "gsk_sgs_plan: coords[d] is NULL for d < dim");
+  if (n > 0x7fffffffll) return fail(ctx, GSK_ERR_UNSUPPORTED, "gsk_sgs_plan: more than 2^31-1 locations");
+  if (vario_kind < 0 || vario_kind > 2) return fail(ctx, GSK_ERR_UNSUPPORTED, "unknown variogram kind");
+  if (!(vario_range > 0.0) || !(vario_sill > 0.0) || !(vario_nugget >= 0.0) || !(gaussian_nugget_eps >= 0.0) ||
+      !(vario_sill - vario_nugget - (vario_kind == GSK_VARIO_GAUSSIAN ? gaussian_nugget_eps : 0.0) > 0.0))
+    return fail(ctx, GSK_ERR_INVALID, "range and sill must be > 0, the nugget below the sill");
+  if (max_neighbors < 1 || min_neighbors < 0 || !std::isfinite(mean))
+    return fail(ctx, GSK_ERR_INVALID, "gsk_sgs_plan: max_neighbors >= 1, min_neighbors >= 0, finite mean");
+  if (max_neighbors > GSK_SGS_MAX_NEIGHBORS)
+    return fail(ctx, GSK_ERR_UNSUPPORTED, "gsk_sgs_plan: max_neighbors above 64");
+  if (!(ball_radius != ball_radius) && !(ball_radius > 0.0))
+    return fail(ctx, GSK_ERR_INVALID, "gsk_sgs_plan: ball_radius must be > 0 (or NaN for none)");
+  GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  free_plan(ctx);  // the buffers are shared with the Kriging plans
+  const GskVario vg = make_vario(vario_kind, vario_range, vario_sill, vario_nugget, gaussian_nugget_eps);
+  const int k = (int)std::min<int64_t>(max_neighbors, n);
+  int rc = gsk_sgs_plan_impl(ctx, dim, n, coords, (const long long *)rank, vg, mean, min_neighbors, k, ball_radius);
+  if (rc != GSK_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    free_plan(ctx);
+  }
+  return rc;
+} catch (const std::bad_alloc &) {  // no exception may cross the C ABI
+  return fail(ctx, GSK_ERR_NOMEM, "gsk_sgs_plan: out of host memory");
+} catch (const std::exception &e) {
+  return fail(ctx, GSK_ERR_STATE, std::string("gsk_sgs_plan: ") + e.what());
+}
+
+extern "C" GSK_API int gsk_sgs_sample(gsk_ctx *ctx, int n_realizations, const double *values, const double *z,
+                                      double *out) try {
+  if (!ctx) return GSK_ERR_INVALID;
+  if (!ctx->sgs) return fail(ctx, GSK_ERR_STATE, "gsk_sgs_sample called before gsk_sgs_plan");
+  if (n_realizations < 1 || !z || !out) return fail(ctx, GSK_ERR_INVALID, "gsk_sgs_sample: n_realizations >= 1, z and out required");
+  GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  return gsk_sgs_sample_impl(ctx, n_realizations, values, z, out);
+} catch (const std::bad_alloc &) {
+  return fail(ctx, GSK_ERR_NOMEM, "gsk_sgs_sample: out of host memory");
+} catch (const std::exception &e) {
+  return fail(ctx, GSK_ERR_STATE, std::string("gsk_sgs_sample: ") + e.what());
+}
+
+extern "C" GSK_API int gsk_sgs_weights(gsk_ctx *ctx, int32_t *nneigh_out, int32_t *neigh_idx_out, double *weights_out,
+                                       double *sigma_out) {
+  if (!ctx) return GSK_ERR_INVALID;
+  if (!ctx->sgs) return fail(ctx, GSK_ERR_STATE, "gsk_sgs_weights called before gsk_sgs_plan");
+  GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return gsk_sgs_weights_impl(ctx, nneigh_out, neigh_idx_out, weights_out, sigma_out);
 }
 
 extern "C" GSK_API int gsk_measure_fp64_peak(gsk_ctx *ctx, double *dfma_tflops, double *dmma_tflops) {

@@ -73,13 +73,14 @@ __global__ void scan_kernel(const int *__restrict__ counts, long long ncells, in
 
 __global__ void scatter_kernel(const double4 *__restrict__ rec_orig, const int *__restrict__ cell_of, long long n,
                                const int *__restrict__ cell_start, int *__restrict__ cursor,
-                               double4 *__restrict__ rec_sorted) {
+                               double4 *__restrict__ rec_sorted, int rank_in_w) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int c = cell_of[i];
   int slot = cell_start[c] + atomicAdd(&cursor[c], 1);
   double4 r = rec_orig[i];
-  r.w = __longlong_as_double((long long)i);
+  const long long hi = rank_in_w ? (__double_as_longlong(r.w) & ~0xffffffffll) : 0ll;  // ranked search: (rank + 1) << 32
+  r.w = __longlong_as_double(hi | (long long)i);
   rec_sorted[slot] = r;
 }
 
@@ -104,7 +105,7 @@ __global__ void cell_sort_kernel(double4 *__restrict__ rec_sorted, const int *__
 }  // namespace
 
 int gsk_build_bins(gsk_ctx *ctx, const double *hx, const double *hy, const double *hz, const double *hv, long long n,
-                   int dim, int k) {
+                   int dim, int k, bool rank_in_w) {
   // ---- bounding box and bin lattice (host, O(n)) ----
   const double *h[3] = {hx, hy, hz};
   double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
@@ -204,7 +205,7 @@ int gsk_build_bins(gsk_ctx *ctx, const double *hx, const double *hy, const doubl
   unsigned gn = (unsigned)((n + TB - 1) / TB);
   count_kernel<<<gn, TB, 0, st>>>(ctx->d_rec_orig, n, b, cell_of, counts);
   scan_kernel<<<1, 1024, 0, st>>>(counts, ncells, ctx->d_cell_start);
-  scatter_kernel<<<gn, TB, 0, st>>>(ctx->d_rec_orig, cell_of, n, ctx->d_cell_start, cursor, ctx->d_rec_sorted);
+  scatter_kernel<<<gn, TB, 0, st>>>(ctx->d_rec_orig, cell_of, n, ctx->d_cell_start, cursor, ctx->d_rec_sorted, rank_in_w ? 1 : 0);
   cell_sort_kernel<<<(unsigned)((ncells + TB - 1) / TB), TB, 0, st>>>(ctx->d_rec_sorted, ctx->d_cell_start, ncells);
   GSK_CUDA_CHECK(ctx, cudaGetLastError());
   // the pinned staging buffer is reused by the next plan: wait for the upload (kernels may still run)

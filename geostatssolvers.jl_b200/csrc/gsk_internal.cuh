@@ -115,12 +115,14 @@ struct GskSearchArgs {
   int scap;        // staged records per chunk
   int *nn;         // out: neighbours per target
   int *nbr;        // out: count × k original indices sorted by (d², idx), −1 padded
+  const int *trank;  // ranked search (sgs.cu) only: rank + 1 of every target; records carry theirs in the high half of w
 };
 
 // ---------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------
 struct GlobalPlan;  // global.cu
+struct SgsPlan;     // sgs.cu
 
 // cached device buffers: grown on demand, never shrunk, released in gsk_destroy — so that repeated
 // gsk_plan / gsk_krige calls do not pay cudaMalloc/cudaFree (which synchronise the device)
@@ -184,6 +186,7 @@ struct gsk_ctx {
   unsigned long long key_geom = 0, key_vals = 0;
 
   GlobalPlan *gplan = nullptr;
+  SgsPlan *sgs = nullptr;  // sequential Gaussian simulation plan (sgs.cu)
 
   // LU Gaussian simulation plan (global.cu: gsk_lu_plan_impl): factor of the joint covariance, [L11⁻¹z1; w2] and y
   long long lu_n = 0, lu_nd = 0, lu_np = 0;
@@ -207,11 +210,12 @@ struct gsk_ctx {
 int gsk_buf(gsk_ctx *ctx, GskBufId id, size_t bytes, void **out);
 int gsk_host_stage(gsk_ctx *ctx, size_t bytes, void **out);
 // bins.cu
+// rank_in_w: hv[i] carries (rank + 1) << 32 as bits; the sorted records keep it in the high half of w (ranked search)
 int gsk_build_bins(gsk_ctx *ctx, const double *hx, const double *hy, const double *hz, const double *hv, long long n,
-                   int dim, int k);
+                   int dim, int k, bool rank_in_w = false);
 // search.cu
 int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long count, int *d_nn, int *d_nbr,
-                      int *launches);
+                      int *launches, const int *d_trank = nullptr);
 // estim.cu: the IDW / LWR per-location bodies on the neighbour lists (or on all samples when k == 0)
 int gsk_launch_simple_solver(gsk_ctx *ctx, cudaStream_t st, long long first, long long count, const int *d_nn,
                              const int *d_nbr, long long out_off, int *d_nn_out, int *launches);
@@ -230,6 +234,12 @@ int gsk_lu_sample_impl(gsk_ctx *ctx, const double *w, double *y_out);  // rec_or
 int gsk_points_sort(gsk_ctx *ctx, long long first, long long count, int **perm, double **sx, double **sy, double **sz);
 int gsk_points_unscatter(gsk_ctx *ctx, const int *perm, long long count, const double *ms, const double *vs,
                          const GskOut &out, const int *nn_s, int *nn_out, const int *nbr_s, int *nbr_out, int k);
+// sgs.cu
+int gsk_sgs_plan_impl(gsk_ctx *ctx, int dim, long long n, const double *const *coords, const long long *rank,
+                      const GskVario &vg, double mean, int min_neighbors, int k, double ball_radius);
+int gsk_sgs_sample_impl(gsk_ctx *ctx, int nreal, const double *values, const double *z, double *out);
+int gsk_sgs_weights_impl(gsk_ctx *ctx, int *nn_out, int *nbr_out, double *lam_out, double *sig_out);
+void gsk_sgs_free(gsk_ctx *ctx);
 // peak.cu
 int gsk_peak_measure(gsk_ctx *ctx, double *dfma, double *dmma);
 

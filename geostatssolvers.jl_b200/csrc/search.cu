@@ -86,7 +86,10 @@ __device__ __forceinline__ int block_excl_scan(int v, int *warp_buf, int *total)
 // HEAP selects how a thread keeps its k best candidates: an ascending list with insertion (cheap for small k,
 // O(k) per accepted candidate) or a binary max-heap (O(log k) per accepted candidate, heap-sorted once at the
 // end) for large k.
-template <int TX, int TY, int TZ, int DIM, bool HEAP>
+// RANKED (sequential simulation, sgs.cu): records carry a rank in the high 32 bits of w next to the index, the target
+// its own rank, and only records of LOWER rank are candidates — the `mask = simulated` of the reference's sequential
+// loop (ref: src/simulation/seq.jl:105), evaluated for every location of the path at once.
+template <int TX, int TY, int TZ, int DIM, bool HEAP, bool RANKED = false>
 __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
   static_assert(TX * TY * TZ == NT, "tile must hold NT targets");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
   double tc[3] = {0.0, 0.0, 0.0};
   long long lin = -1;
   bool active = false;
+  int my_rank = 0;  // RANKED only
   int b0[3] = {0, 0, 0}, b1[3] = {0, 0, 0};  // bins overlapped by the tile's targets
   if (tg.is_grid) {
     int tile = blockIdx.x;
@@ -147,6 +151,7 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
         tc[d] = tg.pts[d][lin];
         mb[d] = bin_clamp(tc[d], bn.lo[d], bn.inv[d], bn.nb[d]);
       }
+      if (RANKED) my_rank = a.trank[lin];
     }
     if (tid < 6) sh_bb[tid] = (tid < 3) ? 0x7fffffff : -1;
     __syncthreads();
@@ -254,7 +259,9 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
           };
           auto consider = [&](const double d2, const double w) {
             if (d2 > worst) return;
-            const int oi = (int)__double_as_longlong(w);
+            const long long wl = __double_as_longlong(w);
+            if (RANKED && (int)(wl >> 32) >= my_rank) return;
+            const int oi = (int)wl;
             if (d2 == worst && oi > worst_i) return;
 #define TD(sl) topd[(size_t)(sl) * NT + tid]
 #define TI(sl) topi[(size_t)(sl) * NT + tid]
@@ -431,8 +438,9 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
 }  // namespace
 
 int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long count, int *d_nn, int *d_nbr,
-                      int *launches) {
+                      int *launches, const int *d_trank) {
   GskSearchArgs a{};
+  a.trank = d_trank;
   a.tg = ctx->tg;
   a.bins = ctx->bins;
   a.k = ctx->prob.max_neighbors;
@@ -501,7 +509,17 @@ int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long 
     e = cudaFuncSetAttribute(search_kernel<TX, TY, TZ, D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e == cudaSuccess) search_kernel<TX, TY, TZ, D, H><<<nblocks, NT, smem, st>>>(a);                           \
   } while (0)
-  if (dim == 1) {
+#define GSK_LAUNCH_RANKED(D, H)                                                                                    \
+  do {                                                                                                             \
+    e = cudaFuncSetAttribute(search_kernel<NT, 1, 1, D, H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e == cudaSuccess) search_kernel<NT, 1, 1, D, H, true><<<nblocks, NT, smem, st>>>(a);                       \
+  } while (0)
+  if (d_trank) {  // explicit points only (the tile shape is unused on that branch)
+    if (ctx->tg.is_grid) { ctx->err = "ranked search needs explicit points"; return GSK_ERR_STATE; }
+    if (dim == 1) { if (heap) GSK_LAUNCH_RANKED(1, true); else GSK_LAUNCH_RANKED(1, false); }
+    else if (dim == 2) { if (heap) GSK_LAUNCH_RANKED(2, true); else GSK_LAUNCH_RANKED(2, false); }
+    else { if (heap) GSK_LAUNCH_RANKED(3, true); else GSK_LAUNCH_RANKED(3, false); }
+  } else if (dim == 1) {
     if (heap) GSK_LAUNCH_SEARCH(NT, 1, 1, 1, true); else GSK_LAUNCH_SEARCH(NT, 1, 1, 1, false);
   } else if (dim == 2) {
     if (heap) GSK_LAUNCH_SEARCH(16, 8, 1, 2, true); else GSK_LAUNCH_SEARCH(16, 8, 1, 2, false);
@@ -509,6 +527,7 @@ int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long 
     if (heap) GSK_LAUNCH_SEARCH(8, 4, 4, 3, true); else GSK_LAUNCH_SEARCH(8, 4, 4, 3, false);
   }
 #undef GSK_LAUNCH_SEARCH
+#undef GSK_LAUNCH_RANKED
   GSK_CUDA_CHECK(ctx, e);
   GSK_CUDA_CHECK(ctx, cudaGetLastError());
   if (launches) *launches += 1;

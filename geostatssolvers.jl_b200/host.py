@@ -719,4 +719,6 @@ def solve(problem: EstimationProblem, solver, ctx: Optional[_abi.Context] = None
         return _sim.solve_fftgs(problem, solver, ctx)
     if isinstance(solver, _sim.LUGS):
         return _sim.solve_lugs(problem, solver, ctx)
+    if isinstance(solver, _sim.SGS):
+        return _sim.solve_sgs(problem, solver, ctx)
     raise TypeError(f"solve: unsupported solver {type(solver).__name__}")

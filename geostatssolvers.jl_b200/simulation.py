@@ -296,3 +296,103 @@ def solve_lugs(problem: SimulationProblem, solver: LUGS, ctx: Optional[_abi.Cont
     pre = preprocess_lugs(problem, solver, var, ctx)
     ns = len(pre["slocs"])
     return [georef({var: lusim(ctx, pre, solver.rng.standard_normal(ns))}, problem.domain()) for _ in range(problem.nreals())]
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Sequential Gaussian simulation — ref src/simulation/sgs.jl (parameters, estimator, marginal) and
+# src/simulation/seq.jl (the loop).
+#   preprocess  sgs.jl:56-89 → seq.jl:42-74   SimpleKriging(variogram, mean), Normal(mean, √sill), searcher_ui
+#   solvesingle seq.jl:76-141                 for ind in traverse(pdomain, path): masked search → fit → draw
+# The masked search, the fit and the kriging weights of EVERY location do not depend on the simulated values; they
+# run once, in parallel, in libgskrige.so (gsk_sgs_plan) and stay resident. A realisation is then the cheap
+# recurrence over the path (gsk_sgs_sample), and all `nreals` realisations run at the same time.
+# --------------------------------------------------------------------------------------------------------------
+_SGS_DEFAULTS = dict(variogram=None, mean=0.0, path=None, minneighbors=1, maxneighbors=10, neighborhood=None, distance=None)
+SGS_MAX_NEIGHBORS = 64
+
+
+class SGS:
+    """``SGS(z=dict(variogram=SphericalVariogram(range=35.0), neighborhood=MetricBall(10.0)), rng=2017)`` —
+    parameters: ref sgs.jl:44-54. `init` is NearestInit (the only one the reference's tests use)."""
+
+    def __init__(self, *pairs, rng=None, **kwpairs):
+        self.vparams = {}
+        for item in list(pairs) + list(kwpairs.items()):
+            for var, params in (list(item.items()) if isinstance(item, dict) else [item]):
+                unknown = set(params) - set(_SGS_DEFAULTS)
+                if unknown:
+                    raise TypeError(f"unknown SGS parameter(s) {sorted(unknown)} for variable {var}")
+                self.vparams[var] = dict(params)
+        self.rng = rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
+
+    def params(self, var):
+        p = dict(_SGS_DEFAULTS)
+        p.update(self.vparams.get(var, {}))
+        if p["variogram"] is None:
+            p["variogram"] = GaussianVariogram()
+        if p["distance"] is None:
+            p["distance"] = Euclidean()
+        if p["path"] is None:
+            from .host import LinearPath
+            p["path"] = LinearPath()
+        return p
+
+
+def preprocess_sgs(problem: SimulationProblem, solver: SGS, var: str, ctx: _abi.Context) -> dict:
+    """ref sgs.jl:56-89 + seq.jl:42-74 for one variable, plus everything of the loop (seq.jl:102-127) that does not
+    depend on the simulated values: the plan is resident in `ctx` afterwards"""
+    from .host import traverse
+    pdomain = problem.domain()
+    p = solver.params(var)
+    gamma = p["variogram"]
+    if not isinstance(gamma, _Variogram) or gamma.kind < 0:
+        raise _unsupported(f"variogram {type(gamma).__name__}")
+    if not isinstance(p["distance"], Euclidean):
+        raise _unsupported("non-Euclidean `distance`")
+    npts = pdomain.nelements()
+    searcher = searcher_ui(pdomain, p["maxneighbors"], p["distance"], p["neighborhood"])   # seq.jl:66
+    if searcher.k > SGS_MAX_NEIGHBORS:
+        raise _unsupported(f"maxneighbors > {SGS_MAX_NEIGHBORS} in sequential simulation")
+    radius = searcher.ball.radius() if isinstance(searcher, KBallSearch) else float("nan")
+    # initbuff(pdomain, pvars, NearestInit(), data=pdata): buffer and mask (seq.jl:88)
+    values = np.zeros(npts)
+    mask = np.zeros(npts, dtype=bool)
+    pdata = problem.data()
+    if pdata is not None and var in pdata.table:
+        cells, kept = _nearest_cells(pdomain, pdata.domain.centroids())
+        col = np.asarray(pdata.table[var], dtype=np.float64)[kept]
+        good = ~np.isnan(col)                                       # missing values are not copied into the buffer
+        values[cells[good]] = col[good]
+        mask[cells[good]] = True
+    # traverse(pdomain, path), skipping the locations that hold data (seq.jl:102-103)
+    visit = traverse(pdomain, p["path"])
+    visit = np.arange(npts, dtype=np.int64) if visit is None else np.asarray(visit, dtype=np.int64)
+    visit = visit[~mask[visit]]
+    rank = np.full(npts, -1, dtype=np.int64)
+    rank[visit] = np.arange(len(visit), dtype=np.int64)
+    ctx.sgs_plan(pdomain.centroids(), rank, vario_kind=gamma.kind, vario_range=gamma.range, vario_sill=gamma.sill,
+                 vario_nugget=gamma.nugget, mean=float(p["mean"]), min_neighbors=int(p["minneighbors"]),
+                 max_neighbors=int(searcher.k), ball_radius=radius)
+    return dict(values=values, mask=mask, visit=visit, rank=rank, npts=npts)
+
+
+def sgs_draws(pre: dict, rng: np.random.Generator, nreals: int) -> np.ndarray:
+    """the standard normal draws of `nreals` realisations, laid out per location: the p-th draw of a realisation belongs
+    to the p-th visited location (seq.jl:110,130 draw one number per visited location, in path order)"""
+    z = np.zeros((nreals, pre["npts"]))
+    for r in range(nreals):
+        z[r, pre["visit"]] = rng.standard_normal(len(pre["visit"]))
+    return z
+
+
+def solve_sgs(problem: SimulationProblem, solver: SGS, ctx: Optional[_abi.Context] = None, z: Optional[np.ndarray] = None):
+    """``solve(problem, SGS(...))`` for one variable — a list of `nreals` GeoTables. `z` (nreals × nelements) overrides
+    the draws (parity tests hand the oracle the same numbers)."""
+    ctx = ctx or default_context()
+    var = problem.variables()[0]
+    pre = preprocess_sgs(problem, solver, var, ctx)
+    nreals = problem.nreals()
+    if z is None:
+        z = sgs_draws(pre, solver.rng, nreals)
+    reals = ctx.sgs_sample(np.asarray(z, dtype=np.float64).reshape(nreals, pre["npts"]), values=pre["values"])
+    return [georef({var: reals[r]}, problem.domain()) for r in range(nreals)]

@@ -228,6 +228,30 @@ GSK_API int gsk_lu_plan(gsk_ctx *ctx, int dim, int64_t n_data, int64_t n_sim, co
  * ρ·w₁ + √(1−ρ²)·w₂, lu.jl:213). y_out (n_data + n_sim): the data values, then d₂ + L₂₂·w (lu.jl:209-219) */
 GSK_API int gsk_lu_sample(gsk_ctx *ctx, const double *w, double *y_out);
 
+/* ---- sequential Gaussian simulation: replaces the simulation loop of SeqSim (ref: src/simulation/seq.jl:102-135) with
+ *      the Simple Kriging estimator and the Normal(mean, √sill) marginal SGS gives it (ref: src/simulation/sgs.jl:62-84) --
+ * coords[d] hold the centroids of the domain's n elements (seq.jl:91). rank[i] = -1: element i holds data (the buffer
+ * NearestInit filled, seq.jl:88; its value is passed with every sample call); otherwise rank[i] is the 0-based position
+ * of element i in traverse(pdomain, path) among the elements without data (a permutation of 0..m-1).
+ * What the loop computes for element i before it draws — the max_neighbors nearest elements among the data and the
+ * elements of lower rank (search! with mask = simulated, seq.jl:105; ball_radius NaN: KNearestSearch, else KBallSearch),
+ * their Simple Kriging weights and the conditional standard deviation — depends on the geometry and the path only, so
+ * the plan computes it for ALL elements in parallel and keeps it resident. max_neighbors <= 64. */
+GSK_API int gsk_sgs_plan(gsk_ctx *ctx, int dim, int64_t n, const double *const *coords, const int64_t *rank,
+                         int vario_kind, double vario_range, double vario_sill, double vario_nugget,
+                         double gaussian_nugget_eps, double mean, int min_neighbors, int max_neighbors,
+                         double ball_radius);
+/* n_realizations realisations at once (one warp each). values (n, may be NULL when there is no data): read where
+ * rank < 0. z (n_realizations × n): the standard normal draw of every element (the caller's RNG; seq.jl:110,130:
+ * rand(rng, Normal(μ, σ)) = μ + σ·randn(rng), so the draw made at path position p goes to z[r·n + order[p]]).
+ * out (n_realizations × n): the data values, and for the others mean + Σ_j λ_ij (out[n_ij] − mean) + σ_i z_i — or
+ * mean + √sill·z_i where fewer than min_neighbors were found or the factorisation failed (seq.jl:108-110,126-128). */
+GSK_API int gsk_sgs_sample(gsk_ctx *ctx, int n_realizations, const double *values, const double *z, double *out);
+/* the plan's per-element neighbour counts (n), neighbour indices (n × k, -1 padded; k = min(max_neighbors, n)),
+ * weights (n × k) and conditional standard deviations (n); any pointer may be NULL */
+GSK_API int gsk_sgs_weights(gsk_ctx *ctx, int32_t *nneigh_out, int32_t *neigh_idx_out, double *weights_out,
+                            double *sigma_out);
+
 /* ---- host helpers shared by every binding ------------------------------------------ */
 /* number of targets of the problem's domain (grid product or n_points) */
 GSK_API int64_t gsk_num_targets(const gsk_problem *prob);

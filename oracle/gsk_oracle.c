@@ -751,6 +751,82 @@ int gsk_oracle_search(const gsk_problem *p, int32_t *nneigh_out, int32_t *neigh_
   return GSK_OK;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Sequential Gaussian simulation: the loop of solvesingle(problem, covars, ::SeqSim, preproc)
+ * (ref: src/simulation/seq.jl:102-135) with the estimator and marginal SGS sets up
+ * (ref: src/simulation/sgs.jl:62-69: SimpleKriging(variogram, mean), Normal(mean, √sill)).
+ * coords: the centroids of the domain (seq.jl:91); rank[i] < 0: data (mask true after initbuff,
+ * seq.jl:88), else the position of i in traverse(pdomain, path) among the others. z[i]: the
+ * standard normal draw used at element i (rand(rng, Normal(μ,σ)) = μ + σ·randn(rng)).
+ * Optional outputs per element: neighbour count, indices (n × k), weights (n × k), σ.
+ * ---------------------------------------------------------------------------------------- */
+int gsk_oracle_sgs(int dim, int64_t n, const double *const *coords, const int64_t *rank, int vario_kind,
+                   double vario_range, double vario_sill, double vario_nugget, double gaussian_nugget_eps, double mean,
+                   int min_neighbors, int max_neighbors, double ball_radius, const double *values, const double *z,
+                   double *out, int32_t *nneigh_out, int32_t *neigh_idx_out, double *weights_out, double *sigma_out) {
+  if (dim < 1 || dim > 3 || n < 1 || !coords || !rank || !z || !out || max_neighbors < 1) return GSK_ERR_INVALID;
+  int k = max_neighbors < n ? max_neighbors : (int)n;
+  gsk_problem pr;
+  memset(&pr, 0, sizeof(pr));
+  pr.dim = dim;
+  pr.n_samples = n;
+  pr.vario_kind = vario_kind; pr.vario_range = vario_range; pr.vario_sill = vario_sill; pr.vario_nugget = vario_nugget;
+  pr.gaussian_nugget_eps = gaussian_nugget_eps;
+  pr.estimator = GSK_EST_SIMPLE;
+  pr.sk_mean = mean;
+  pr.n_support = 1; /* predictprob at the point pset[ind] (seq.jl:124) */
+  pr.flags = GSK_FLAG_CLAMP_VARIANCE;
+  pr.values = out; /* the realisation buffer doubles as the neighbours' values (seq.jl:116) */
+  vario_t v = vario_from(&pr);
+  double *xyz = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+  for (int64_t i = 0; i < n; i++)
+    for (int d = 0; d < 3; d++) xyz[3 * i + d] = (d < dim) ? coords[d][i] : 0.0;
+  int64_t m = 0;
+  for (int64_t i = 0; i < n; i++) if (rank[i] >= 0) m++;
+  int64_t *order = (int64_t *)malloc(sizeof(int64_t) * (size_t)(m > 0 ? m : 1));
+  unsigned char *simulated = (unsigned char *)calloc((size_t)n, 1);
+  for (int64_t i = 0; i < n; i++) {
+    if (rank[i] >= 0) { if (rank[i] >= m) { free(xyz); free(order); free(simulated); return GSK_ERR_INVALID; } order[rank[i]] = i; }
+    else { simulated[i] = 1; out[i] = values ? values[i] : 0.0; }
+  }
+  int use_ball = !(ball_radius != ball_radius);
+  cand_t *best = (cand_t *)malloc(sizeof(cand_t) * (size_t)k);
+  int32_t *nb = (int32_t *)malloc(sizeof(int32_t) * (size_t)k);
+  fitted_t f;
+  f.A = (double *)malloc(sizeof(double) * (size_t)k * k);
+  f.piv = NULL;
+  double *rhs = (double *)malloc(sizeof(double) * (size_t)k), *sol = (double *)malloc(sizeof(double) * (size_t)k);
+  for (int64_t p = 0; p < m; p++) { /* for ind in traverse(pdomain, path); if !simulated[ind] */
+    int64_t ind = order[p];
+    const double *c = xyz + 3 * ind;
+    /* search!(neighbors, pset[ind], searcher, mask=simulated) */
+    int cnt = 0;
+    for (int64_t j = 0; j < n; j++)
+      if (simulated[j]) topk_insert(best, &cnt, k, dist2(dim, c, xyz + 3 * j), (int32_t)j);
+    int nn = cnt;
+    if (use_ball) { nn = 0; while (nn < cnt && sqrt(best[nn].d2) <= ball_radius) nn++; }
+    double mu = mean, sd = sqrt(vario_sill); /* marginal */
+    int fitted = 0;
+    if (nn >= min_neighbors && nn >= 1) {
+      for (int i = 0; i < nn; i++) nb[i] = best[i].idx;
+      fit_system(&pr, &v, xyz, nb, nn, 0, NULL, &f);
+      double mu_c, s2;
+      predict(&pr, &v, xyz, nb, &f, NULL, c, rhs, sol, &mu_c, &s2);
+      if (mu_c == mu_c && s2 == s2) { mu = mu_c; sd = sqrt(s2); fitted = 1; } /* status(fitted) */
+    }
+    out[ind] = mu + sd * z[ind];
+    simulated[ind] = 1;
+    if (nneigh_out) nneigh_out[ind] = fitted ? nn : 0;
+    if (sigma_out) sigma_out[ind] = sd;
+    for (int i = 0; i < k; i++) {
+      if (neigh_idx_out) neigh_idx_out[ind * (int64_t)k + i] = (fitted && i < nn) ? nb[i] : -1;
+      if (weights_out) weights_out[ind * (int64_t)k + i] = (fitted && i < nn) ? sol[i] : 0.0;
+    }
+  }
+  free(best); free(nb); free(f.A); free(rhs); free(sol); free(xyz); free(order); free(simulated);
+  return GSK_OK;
+}
+
 int gsk_oracle_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

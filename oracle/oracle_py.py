@@ -39,6 +39,9 @@ def load():
         lib.gsk_oracle_uk_exponents.argtypes = [C.c_int, C.c_int, vp, C.c_int]
         lib.gsk_oracle_uk_exponents.restype = C.c_int
         lib.gsk_oracle_threads.restype = C.c_int
+        lib.gsk_oracle_sgs.argtypes = ([C.c_int, C.c_int64, vp, vp, C.c_int] + [C.c_double] * 5 + [C.c_int, C.c_int, C.c_double]
+                                       + [vp] * 7)
+        lib.gsk_oracle_sgs.restype = C.c_int
         _lib = lib
     return _lib
 
@@ -74,6 +77,32 @@ def search(spec, search=SEARCH_BRUTE, nthreads=0):
     if rc != 0:
         raise RuntimeError(f"gsk_oracle_search failed: {rc}")
     return nneigh, idx, d2
+
+
+def sgs(coords, rank, *, vario_kind, vario_range, vario_sill=1.0, vario_nugget=0.0, gaussian_nugget_eps=1e-6, mean=0.0,
+        min_neighbors=1, max_neighbors=10, ball_radius=float("nan"), values=None, z=None):
+    """One realisation of the sequential loop (seq.jl:102-135); returns (out, nneigh, idx, weights, sigma)."""
+    lib = load()
+    cs = [np.ascontiguousarray(c, dtype=np.float64) for c in coords]
+    n = cs[0].shape[0]
+    k = min(max_neighbors, n)
+    arr = (C.c_void_p * 3)(*[c.ctypes.data for c in cs] + [None] * (3 - len(cs)))
+    rank = np.ascontiguousarray(rank, dtype=np.int64)
+    vals = np.ascontiguousarray(values, dtype=np.float64) if values is not None else None
+    z = np.ascontiguousarray(z, dtype=np.float64)
+    out = np.empty(n)
+    nn = np.zeros(n, dtype=np.int32)
+    idx = np.full((n, k), -1, dtype=np.int32)
+    lam = np.zeros((n, k))
+    sig = np.zeros(n)
+    rc = lib.gsk_oracle_sgs(len(cs), n, C.addressof(arr), rank.ctypes.data, int(vario_kind), float(vario_range),
+                            float(vario_sill), float(vario_nugget), float(gaussian_nugget_eps), float(mean),
+                            int(min_neighbors), int(max_neighbors), float(ball_radius),
+                            vals.ctypes.data if vals is not None else None, z.ctypes.data, out.ctypes.data,
+                            nn.ctypes.data, idx.ctypes.data, lam.ctypes.data, sig.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"gsk_oracle_sgs failed: {rc}")
+    return out, nn, idx, lam, sig
 
 
 def uk_exponents(degree, dim):
