@@ -9,13 +9,18 @@
 //     computes them for ALL locations at once: a rank-masked search (search.cu, RANKED: a record is a candidate only
 //     if its rank in the path is lower than the target's; data locations have the lowest rank) and one small SPD
 //     solve per location (sgs_weights_kernel, one thread per location).
-//   * the values follow the recurrence v_i = μ + Σ_j λ_ij (v_n(i,j) − μ) + σ_i z_i in path order
-//     (sgs_recurrence_kernel: one warp per realisation, lanes over the neighbours; the realisations of an ensemble run
-//     on different SMs at the same time).
+//   * the values follow the recurrence v_i = μ + Σ_j λ_ij (v_n(i,j) − μ) + σ_i z_i. The neighbour lists make it a DAG
+//     over the locations; its levels (level = 1 + the deepest simulated neighbour) are computed once with the plan,
+//     and a realisation is evaluated level by level: every location of a level is independent of the others
+//     (sgs_level_kernel, one thread per location and realisation; runs of small levels share one launch,
+//     sgs_run_kernel). Only when the DAG is nearly a chain (a linear path on a line) the path is walked by one warp
+//     per realisation instead (sgs_recurrence_kernel). The results do not depend on the schedule.
 // The draws z come from the caller's generator (rand(rng, Normal(μ, σ)) = μ + σ·randn(rng), one per location in path
 // order), so the library holds no random state.
 #include <math.h>
 
+#include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <vector>
 
@@ -33,6 +38,17 @@ struct SgsPlan {
   int *isdata = nullptr;  // n: 1 where the value is given
   double *vals = nullptr, *z = nullptr, *out = nullptr;  // sample buffers (grown on demand)
   size_t cap_real = 0;
+  // level schedule (depth == 0: not used, the path is walked by sgs_recurrence_kernel)
+  int depth = 0;
+  int *lv_start = nullptr;  // depth + 1: positions of level l are [lv_start[l], lv_start[l + 1])
+  int *lv_loc = nullptr;    // m: location at position pos (positions are sorted by level)
+  int *lv_nn = nullptr;     // m
+  int *lv_nbr = nullptr;    // k × m, neighbour j of position pos at [j · m + pos]
+  double *lv_lam = nullptr; // k × m
+  double *lv_sig = nullptr; // m
+  struct Seg { int l0, l1, wide; };  // launch schedule: one wide level, or a run [l0, l1) of small levels
+  std::vector<Seg> segs;
+  std::vector<int> h_lv_start;
 };
 
 namespace {
@@ -176,6 +192,82 @@ __global__ void __launch_bounds__(32) sgs_recurrence_kernel(const int *__restric
   }
 }
 
+// plan arrays re-ordered by level position, neighbour-major (coalesced for one thread per position)
+__global__ void sgs_to_levels_kernel(const int *__restrict__ lv_loc, long long m, int k, const int *__restrict__ nn,
+                                     const int *__restrict__ nbr, const double *__restrict__ lam, const double *__restrict__ sig,
+                                     int *__restrict__ lv_nn, int *__restrict__ lv_nbr, double *__restrict__ lv_lam,
+                                     double *__restrict__ lv_sig) {
+  long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= m) return;
+  const long long loc = lv_loc[pos];
+  lv_nn[pos] = nn[loc];
+  lv_sig[pos] = sig[loc];
+  for (int j = 0; j < k; ++j) {
+    lv_nbr[(long long)j * m + pos] = nbr[loc * k + j];
+    lv_lam[(long long)j * m + pos] = lam[loc * k + j];
+  }
+}
+
+template <bool SAME_SM>
+__device__ __forceinline__ void sgs_eval_position(long long pos, long long m, long long n, const int *__restrict__ lv_loc,
+                                                  const int *__restrict__ lv_nn, const int *__restrict__ lv_nbr,
+                                                  const double *__restrict__ lv_lam, const double *__restrict__ lv_sig,
+                                                  const double *__restrict__ zr, double mean, double *vr) {
+  const int nn = lv_nn[pos];
+  double acc = 0.0;
+  // eight neighbours at a time: their indices and weights first, then the eight values (independent loads in flight
+  // together — inside a run of levels the latency of this chain is the cost of a level), then the sum in list order
+  for (int j0 = 0; j0 < nn; j0 += 8) {
+    int idx[8];
+    double lm[8], v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool in = j0 + u < nn;
+      idx[u] = in ? lv_nbr[(long long)(j0 + u) * m + pos] : -1;
+      lm[u] = in ? lv_lam[(long long)(j0 + u) * m + pos] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      // inside a run of levels the value may have been written by another thread of this CTA a moment ago: read past L1
+      v[u] = (idx[u] >= 0) ? (SAME_SM ? __ldcg(vr + idx[u]) : vr[idx[u]]) : mean;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc = fma(lm[u], v[u] - mean, acc);
+  }
+  const int loc = lv_loc[pos];
+  const double x = (mean + acc) + lv_sig[pos] * zr[loc];
+  if (SAME_SM) __stcg(vr + loc, x); else vr[loc] = x;
+}
+
+// one level: thread per (position, realisation)
+__global__ void sgs_level_kernel(int pos0, int cnt, long long m, long long n, const int *__restrict__ lv_loc,
+                                 const int *__restrict__ lv_nn, const int *__restrict__ lv_nbr, const double *__restrict__ lv_lam,
+                                 const double *__restrict__ lv_sig, const double *__restrict__ z, double mean,
+                                 double *out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cnt) return;
+  const long long r = blockIdx.y;
+  sgs_eval_position<false>(pos0 + t, m, n, lv_loc, lv_nn, lv_nbr, lv_lam, lv_sig, z + r * n, mean, out + r * n);
+}
+
+// a run of consecutive small levels: one CTA per realisation, a CTA-wide barrier between levels
+__global__ void sgs_run_kernel(int l0, int l1, const int *__restrict__ lv_start, long long m, long long n,
+                               const int *__restrict__ lv_loc, const int *__restrict__ lv_nn, const int *__restrict__ lv_nbr,
+                               const double *__restrict__ lv_lam, const double *__restrict__ lv_sig, const double *__restrict__ z,
+                               double mean, double *out) {
+  const long long r = blockIdx.x;
+  const double *zr = z + r * n;
+  double *vr = out + r * n;
+  int a = lv_start[l0];
+  for (int l = l0; l < l1; ++l) {
+    const int b = lv_start[l + 1];
+    for (int pos = a + threadIdx.x; pos < b; pos += blockDim.x)
+      sgs_eval_position<true>(pos, m, n, lv_loc, lv_nn, lv_nbr, lv_lam, lv_sig, zr, mean, vr);
+    __syncthreads();
+    a = b;
+  }
+}
+
 }  // namespace
 
 void gsk_sgs_free(gsk_ctx *ctx) {
@@ -183,6 +275,7 @@ void gsk_sgs_free(gsk_ctx *ctx) {
   if (!s) return;
   cudaFree(s->nn); cudaFree(s->nbr); cudaFree(s->lam); cudaFree(s->sig); cudaFree(s->order); cudaFree(s->isdata);
   cudaFree(s->vals); cudaFree(s->z); cudaFree(s->out);
+  cudaFree(s->lv_start); cudaFree(s->lv_loc); cudaFree(s->lv_nn); cudaFree(s->lv_nbr); cudaFree(s->lv_lam); cudaFree(s->lv_sig);
   delete s;
   ctx->sgs = nullptr;
 }
@@ -190,6 +283,9 @@ void gsk_sgs_free(gsk_ctx *ctx) {
 int gsk_sgs_plan_impl(gsk_ctx *ctx, int dim, long long n, const double *const *coords, const long long *rank,
                       const GskVario &vg, double mean, int min_neighbors, int k, double ball_radius) {
   cudaStream_t st = ctx->stream;
+  using clk = std::chrono::steady_clock;
+  auto ms_since = [](clk::time_point t) { return std::chrono::duration<double, std::milli>(clk::now() - t).count(); };
+  const clk::time_point t_begin = clk::now();
   // ---- the path: order[p] = location of rank p; ranks must be a permutation of 0..m−1 over the locations without data
   long long m = 0;
   for (long long i = 0; i < n; ++i) if (rank[i] >= 0) ++m;
@@ -257,7 +353,11 @@ int gsk_sgs_plan_impl(gsk_ctx *ctx, int dim, long long n, const double *const *c
   GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(s->isdata, isdata.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
   GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(d_rankp1, rankp1.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
 
+  ctx->timing = gsk_timing{};
+  ctx->timing_pending = false;
+  ctx->timing.ms_plan = ms_since(t_begin);  // path checks, bins, uploads
   // ---- bin-sort the locations, search with the rank mask, solve ----
+  clk::time_point t_phase = clk::now();
   int *perm = nullptr, *nn_s = nullptr, *nbr_s = nullptr;
   double *sx = nullptr, *sy = nullptr, *sz = nullptr;
   if ((rc = gsk_points_sort(ctx, 0, n, &perm, &sx, &sy, &sz)) != GSK_OK) return rc;
@@ -273,6 +373,9 @@ int gsk_sgs_plan_impl(gsk_ctx *ctx, int dim, long long n, const double *const *c
   rc = gsk_launch_search(ctx, st, 0, n, nn_s, nbr_s, &launches, d_trank);
   ctx->tg = tg_saved;
   if (rc != GSK_OK) return rc;
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  ctx->timing.ms_search = ms_since(t_phase);
+  t_phase = clk::now();
 
   const size_t per_thread = sizeof(double) * (size_t)(k * (k + 1) / 2 + k);
   int tpb = 128;
@@ -291,14 +394,75 @@ int gsk_sgs_plan_impl(gsk_ctx *ctx, int dim, long long n, const double *const *c
   sgs_weights_kernel<<<grid, tpb, smem, st>>>(tgs, vg, ctx->d_rec_orig, perm, nn_s, nbr_s, n, k, min_neighbors,
                                              s->sd_marginal, gwork, s->nn, s->nbr, s->lam, s->sig);
   GSK_CUDA_CHECK(ctx, cudaGetLastError());
-  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));  // host vectors above go out of scope
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+  ctx->timing.ms_solve = ms_since(t_phase);
   ctx->timing.launches = launches + 6 + 4 + 2;
+  ctx->timing.targets = m;
+
+  // ---- level schedule of the recurrence: level(i) = 1 + max level of i's simulated neighbours (data: level 0) ----
+  {
+    std::vector<int> h_nn((size_t)n), h_nbr((size_t)n * k), level((size_t)n, 0);
+    GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(h_nn.data(), s->nn, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(h_nbr.data(), s->nbr, sizeof(int) * (size_t)n * k, cudaMemcpyDeviceToHost, st));
+    GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    int depth = 0;
+    for (long long p = 0; p < m; ++p) {
+      const size_t i = (size_t)order[(size_t)p];
+      int lv = 0;
+      const int *nb = &h_nbr[i * k];
+      for (int j = 0; j < h_nn[i]; ++j) lv = std::max(lv, level[(size_t)nb[j]]);
+      level[i] = lv + 1;
+      depth = std::max(depth, lv + 1);
+    }
+    // a nearly sequential DAG gains nothing from levels: one warp per realisation walks the path instead
+    if ((long long)depth * 8 <= m || m < 4096) {
+      std::vector<int> start((size_t)depth + 1, 0), lv_loc((size_t)m);
+      for (long long p = 0; p < m; ++p) ++start[(size_t)level[(size_t)order[(size_t)p]]];  // start[l] = size of level l (1-based)
+      int run = 0;
+      for (int l = 1; l <= depth; ++l) { const int c = start[(size_t)l]; start[(size_t)l - 1] = run; run += c; }
+      start[(size_t)depth] = run;  // start[l-1] = first position of level l  → 0-based levels from here on
+      {
+        std::vector<int> cursor(start.begin(), start.end() - 1);
+        for (long long p = 0; p < m; ++p) {  // path order inside a level
+          const int i = order[(size_t)p];
+          lv_loc[(size_t)cursor[(size_t)level[(size_t)i] - 1]++] = i;
+        }
+      }
+      s->depth = depth;
+      s->h_lv_start = start;
+      GSK_CUDA_CHECK(ctx, cudaMalloc(&s->lv_start, sizeof(int) * ((size_t)depth + 1)));
+      GSK_CUDA_CHECK(ctx, cudaMalloc(&s->lv_loc, sizeof(int) * (size_t)m));
+      GSK_CUDA_CHECK(ctx, cudaMalloc(&s->lv_nn, sizeof(int) * (size_t)m));
+      GSK_CUDA_CHECK(ctx, cudaMalloc(&s->lv_nbr, sizeof(int) * (size_t)m * k));
+      GSK_CUDA_CHECK(ctx, cudaMalloc(&s->lv_lam, sizeof(double) * (size_t)m * k));
+      GSK_CUDA_CHECK(ctx, cudaMalloc(&s->lv_sig, sizeof(double) * (size_t)m));
+      GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(s->lv_start, start.data(), sizeof(int) * ((size_t)depth + 1), cudaMemcpyHostToDevice, st));
+      GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(s->lv_loc, lv_loc.data(), sizeof(int) * (size_t)m, cudaMemcpyHostToDevice, st));
+      sgs_to_levels_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(s->lv_loc, m, k, s->nn, s->nbr, s->lam, s->sig, s->lv_nn,
+                                                                      s->lv_nbr, s->lv_lam, s->lv_sig);
+      GSK_CUDA_CHECK(ctx, cudaGetLastError());
+      // launch schedule: consecutive levels of at most SGS_SMALL positions share one launch
+      const int SGS_SMALL = 1024;
+      for (int l = 0; l < depth;) {
+        if (start[(size_t)l + 1] - start[(size_t)l] > SGS_SMALL) { s->segs.push_back({l, l + 1, 1}); ++l; continue; }
+        int e = l;
+        while (e < depth && start[(size_t)e + 1] - start[(size_t)e] <= SGS_SMALL) ++e;
+        s->segs.push_back({l, e, 0});
+        l = e;
+      }
+      GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+      ctx->timing.launches += 1;
+    }
+  }
+  GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));  // host vectors above go out of scope
+  ctx->timing.ms_total = ms_since(t_begin);          // the rest: level schedule (host) and its upload
   return GSK_OK;
 }
 
 int gsk_sgs_sample_impl(gsk_ctx *ctx, int nreal, const double *values, const double *z, double *out) {
   SgsPlan *s = ctx->sgs;
   cudaStream_t st = ctx->stream;
+  const std::chrono::steady_clock::time_point t_begin = std::chrono::steady_clock::now();
   const size_t n = (size_t)s->n;
   if (s->cap_real < (size_t)nreal) {
     cudaFree(s->z); cudaFree(s->out); cudaFree(s->vals);
@@ -313,13 +477,42 @@ int gsk_sgs_sample_impl(gsk_ctx *ctx, int nreal, const double *values, const dou
   else GSK_CUDA_CHECK(ctx, cudaMemsetAsync(s->vals, 0, sizeof(double) * n, st));
   GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(s->z, z, sizeof(double) * n * nreal, cudaMemcpyHostToDevice, st));
   const long long tot = (long long)n * nreal;
+  cudaEventRecord(ctx->ev[3], st);
   sgs_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(s->vals, s->isdata, s->n, nreal, s->out);
-  sgs_recurrence_kernel<<<(unsigned)nreal, 32, 0, st>>>(s->order, s->m, s->n, s->k, s->nn, s->nbr, s->lam, s->sig, s->z,
-                                                        s->mean, s->out);
+  int launches = 1;
+  if (s->depth > 0) {
+    for (const SgsPlan::Seg &g : s->segs) {
+      if (g.wide) {
+        const int pos0 = s->h_lv_start[(size_t)g.l0], cnt = s->h_lv_start[(size_t)g.l1] - pos0;
+        // realisations in chunks of 65535 (gridDim.y)
+        for (int r0 = 0; r0 < nreal; r0 += 65535) {
+          const dim3 grid((unsigned)((cnt + 127) / 128), (unsigned)std::min(nreal - r0, 65535));
+          sgs_level_kernel<<<grid, 128, 0, st>>>(pos0, cnt, s->m, s->n, s->lv_loc, s->lv_nn, s->lv_nbr, s->lv_lam, s->lv_sig,
+                                                 s->z + (size_t)r0 * n, s->mean, s->out + (size_t)r0 * n);
+          ++launches;
+        }
+      } else {
+        sgs_run_kernel<<<(unsigned)nreal, 256, 0, st>>>(g.l0, g.l1, s->lv_start, s->m, s->n, s->lv_loc, s->lv_nn, s->lv_nbr,
+                                                        s->lv_lam, s->lv_sig, s->z, s->mean, s->out);
+        ++launches;
+      }
+    }
+  } else {
+    sgs_recurrence_kernel<<<(unsigned)nreal, 32, 0, st>>>(s->order, s->m, s->n, s->k, s->nn, s->nbr, s->lam, s->sig, s->z,
+                                                          s->mean, s->out);
+    ++launches;
+  }
   GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  cudaEventRecord(ctx->ev[4], st);
   GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(out, s->out, sizeof(double) * n * nreal, cudaMemcpyDeviceToHost, st));
   GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-  ctx->timing.launches = 2;
+  ctx->timing = gsk_timing{};
+  ctx->timing_pending = false;
+  float ms_k = 0.f;
+  if (cudaEventElapsedTime(&ms_k, ctx->ev[3], ctx->ev[4]) == cudaSuccess) ctx->timing.ms_solve = ms_k;  // the kernels alone
+  ctx->timing.ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  ctx->timing.targets = (long long)s->m * nreal;
+  ctx->timing.launches = launches;
   return GSK_OK;
 }
 
