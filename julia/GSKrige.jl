@@ -11,7 +11,8 @@ module GSKrige
 
 using GeoStatsBase, GeoStatsModels, Variography, Meshes, GeoTables, Tables, Unitful, Distances
 import GeoStatsSolvers                       # kriging_ui / searcher_ui (src/ui.jl) and the solver types are the reference's own
-import GeoStatsSolvers: KrigingSolver, IDWSolver, LWRSolver
+import GeoStatsSolvers: KrigingSolver, IDWSolver, LWRSolver, SGS
+using Random
 import GeoStatsBase: solve, preprocess
 
 # `north_star` spells the solver `Kriging(...)` (the name older GeoStats releases used); the reference's type is
@@ -221,6 +222,50 @@ function solve_b200(problem::EstimationProblem, solver::Union{IDWSolver,LWRSolve
     end
   end
   georef((; μs..., σs...), pdomain)
+end
+
+"""
+drop-in for GeoStatsSolvers.solve(problem, ::SGS) (sgs.jl:56-89 → seq.jl:76-141), one variable: the masked searches, the
+Simple Kriging fits and the weights of every location of the path are computed at once (gsk_sgs_plan); the `nreals`
+realisations are then one gsk_sgs_sample call. The draws are `randn(solver.rng)` in path order — the numbers
+`rand(rng, Normal(μ, σ))` consumes in the reference's loop (seq.jl:110,130), so a seeded solver gives the same
+realisations as the reference up to the rounding of the kriging systems.
+"""
+function solve_b200(problem::SimulationProblem, solver::SGS; ctx=context())
+  pdata = data(problem); pdomain = domain(problem); pvars = variables(problem)
+  N = nelements(pdomain); dim = embeddim(pdomain)
+  X = [Float64[ustrip(coordinates(centroid(pdomain, i))[d]) for i in 1:N] for d in 1:dim]      # seq.jl:91
+  buff, mask = GeoStatsBase.initbuff(pdomain, pvars, solver.init, data=pdata)                 # seq.jl:88
+  reals = []
+  for covars in covariables(problem, solver), var in covars.names
+    p = covars.params[Set([var])]
+    p.distance isa Euclidean || throw(ArgumentError("non-Euclidean `distance` is not supported by the B200 path"))
+    γ = p.variogram
+    searcher = GeoStatsSolvers.searcher_ui(pdomain, p.maxneighbors, p.distance, p.neighborhood)  # seq.jl:66
+    radius = searcher isa KBallSearch ? Float64(ustrip(Meshes.radius(searcher.ball))) : NaN
+    simulated = mask[var]
+    visit = [i for i in traverse(pdomain, p.path) if !simulated[i]]                            # seq.jl:102-103
+    rank = fill(Int64(-1), N); rank[visit] .= 0:(length(visit) - 1)
+    vals = Float64[simulated[i] ? buff[var][i] : 0.0 for i in 1:N]
+    nreals = GeoStatsBase.nreals(problem)
+    z = zeros(N, nreals)
+    for r in 1:nreals, i in visit
+      z[i, r] = randn(solver.rng)
+    end
+    out = Matrix{Float64}(undef, N, nreals)
+    GC.@preserve X rank vals z out begin
+      ptrs = ntuple(d -> d <= dim ? pointer(X[d]) : Ptr{Float64}(C_NULL), 3)
+      check(ctx, ccall((:gsk_sgs_plan, LIB), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Ref{NTuple{3,Ptr{Float64}}}, Ptr{Int64}, Cint, Float64, Float64, Float64, Float64, Float64,
+         Cint, Cint, Float64),
+        ctx.handle, dim, N, ptrs, rank, variokind(γ), ustrip(range(γ)), ustrip(sill(γ)), ustrip(nugget(γ)), 1e-6,
+        Float64(p.mean), p.minneighbors, maxneighbors(searcher), radius))
+      check(ctx, ccall((:gsk_sgs_sample, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        ctx.handle, nreals, vals, z, out))
+    end
+    push!(reals, var => [out[:, r] for r in 1:nreals])
+  end
+  Ensemble(pdomain, Dict(reals))
 end
 
 end # module
