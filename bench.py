@@ -454,6 +454,74 @@ def measure_secondary(env: Env, name: str, dfma, dmma):
     return out
 
 
+def measure_callers(env: Env):
+    """SURVEY §8f rows that sit on the same kernels, through the public API with host buffers (documentation figures,
+    a few seconds in total): the IDW / LWR solvers on the C2 shape, and sequential Gaussian simulation (plan = masked
+    search + weights for the whole path; realisations = level-scheduled recurrence)."""
+    gsk, torch = env.gsk, env.torch
+    out = {}
+    ctx = gsk.Context(env.local_rank)
+    try:
+        base = gsk.synth.config_spec("C2")
+        T = int(np.prod(base.grid_dims))
+        for nm, sv in (("idw", gsk.SOLVER_IDW), ("lwr", gsk.SOLVER_LWR)):
+            spec = gsk.ProblemSpec(coords=base.coords, values=base.values, grid_dims=base.grid_dims, solver=sv, idw_exponent=2.0,
+                                   max_neighbors=20)
+            ctx.krige(spec)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                ctx.krige(spec)
+            dt = (time.perf_counter() - t0) / 3
+            out[nm] = {"workload": f"{nm.upper()} solver, C2 shape (1000x1000 grid, 10 000 samples, maxneighbors=20)",
+                       "value": T / dt, "unit": UNIT, "ms_per_call": dt * 1e3, "api": "gsk_krige, host buffers"}
+        # SGS: 512x512 grid, 100 data, spherical variogram, maxneighbors = 10, random path
+        dims, k, nreal = (512, 512), 10, 64
+        n = dims[0] * dims[1]
+        rng = np.random.default_rng(0)
+        gx, gy = np.meshgrid(np.arange(dims[0]) + 0.5, np.arange(dims[1]) + 0.5)
+        cs = [gx.ravel().copy(), gy.ravel().copy()]
+        data = rng.choice(n, 100, replace=False)
+        order = rng.permutation(n)
+        isdata = np.zeros(n, dtype=bool)
+        isdata[data] = True
+        visit = order[~isdata[order]]
+        rank = np.full(n, -1, dtype=np.int64)
+        rank[visit] = np.arange(len(visit))
+        vals = np.where(isdata, rng.standard_normal(n), 0.0)
+        kw = dict(vario_kind=gsk.VARIO_SPHERICAL, vario_range=20.0, max_neighbors=k)
+        ctx.sgs_plan(cs, rank, **kw)
+        t0 = time.perf_counter()
+        ctx.sgs_plan(cs, rank, **kw)
+        t_plan = time.perf_counter() - t0
+        z = rng.standard_normal((nreal, n))
+        ctx.sgs_sample(z[:1], values=vals)
+        t0 = time.perf_counter()
+        res = ctx.sgs_sample(z, values=vals)
+        t_abi = time.perf_counter() - t0
+        tk = ctx.timing()
+        dz, dv = torch.from_numpy(z).to(env.dev), torch.from_numpy(vals).to(env.dev)
+        dout = torch.empty_like(dz)
+        torch.cuda.synchronize(env.dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.set_stream(env.stream.cuda_stream)
+        ctx.sgs_sample_device(nreal, dv.data_ptr(), dz.data_ptr(), dout.data_ptr())
+        e0.record(env.stream)
+        ctx.sgs_sample_device(nreal, dv.data_ptr(), dz.data_ptr(), dout.data_ptr())
+        e1.record(env.stream)
+        torch.cuda.synchronize(env.dev)
+        ms_dev = e0.elapsed_time(e1)
+        same = bool(np.array_equal(dout.cpu().numpy(), res))
+        out["sgs"] = {"workload": f"SGS, {dims[0]}x{dims[1]} grid, 100 data, spherical variogram, maxneighbors={k}, random path, {nreal} realisations",
+                      "plan_ms": t_plan * 1e3, "value": nreal * n / t_abi, "unit": "simulated locations/s",
+                      "ms_per_call": t_abi * 1e3, "api": "gsk_sgs_sample, pageable host buffers (draws in, realisations out)",
+                      "device_resident": {"value": nreal * n / (ms_dev * 1e-3), "ms_per_call": ms_dev, "launches": int(tk["launches"]),
+                                          "api": "gsk_sgs_sample_device", "same_bytes_as_host_call": same}}
+    except Exception as exc:  # noqa: BLE001 - informational block
+        out["error"] = f"{type(exc).__name__}: {exc}"
+    ctx.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -532,6 +600,12 @@ def main():
                 configs[other] = {"error": f"{type(exc).__name__}: {exc}"}
             env.barrier()
 
+    callers = {}
+    if not args.no_secondary and not args.targets:
+        if env.rank == 0:
+            callers = measure_callers(env)
+        env.barrier()
+
     if env.rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": env.world, "steps": args.steps, "warmup": warm,
@@ -548,6 +622,7 @@ def main():
             "phases_ms": {"plan": plan_ms, "search": search_ms, "solve": solve_ms},
             "wall_s_timed_region": wall,
             "configs": configs,
+            "callers": callers,
         }
         if not args.no_cpu_baseline and env.world == 1:
             import oracle_py as O

@@ -274,6 +274,8 @@ def load_library(path: os.PathLike | None = None):
     lib.gsk_sgs_plan.restype = C.c_int
     lib.gsk_sgs_sample.argtypes = [ctx, C.c_int, _dp, _dp, _dp]
     lib.gsk_sgs_sample.restype = C.c_int
+    lib.gsk_sgs_sample_device.argtypes = [ctx, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.gsk_sgs_sample_device.restype = C.c_int
     lib.gsk_sgs_weights.argtypes = [ctx, _ip, _ip, _dp, _dp]
     lib.gsk_sgs_weights.restype = C.c_int
     lib.gsk_get_timing.argtypes = [ctx, C.POINTER(GskTiming)]
@@ -297,7 +299,7 @@ def load_library(path: os.PathLike | None = None):
 
 EXPORTED_SYMBOLS = [
     "gsk_create", "gsk_destroy", "gsk_last_error", "gsk_set_stream", "gsk_synchronize", "gsk_krige", "gsk_krige_multi", "gsk_krige_multi_release", "gsk_plan",
-    "gsk_execute", "gsk_execute_peers", "gsk_update_values", "gsk_lu_plan", "gsk_lu_sample", "gsk_sgs_plan", "gsk_sgs_sample", "gsk_sgs_weights", "gsk_get_timing", "gsk_set_phase_timing", "gsk_num_targets", "gsk_uk_exponents", "gsk_default_support",
+    "gsk_execute", "gsk_execute_peers", "gsk_update_values", "gsk_lu_plan", "gsk_lu_sample", "gsk_sgs_plan", "gsk_sgs_sample", "gsk_sgs_sample_device", "gsk_sgs_weights", "gsk_get_timing", "gsk_set_phase_timing", "gsk_num_targets", "gsk_uk_exponents", "gsk_default_support",
     "gsk_measure_fp64_peak", "gsk_abi_version",
 ]
 
@@ -420,6 +422,11 @@ class Context:
         out = np.empty_like(z)
         self._check(self.lib.gsk_sgs_sample(self._h, nreal, _ptr(v) if v is not None else None, _ptr(z), _ptr(out)))
         return out
+
+    def sgs_sample_device(self, nreal, d_values, d_z, d_out):
+        """device pointers (ints; d_values may be 0 without data); asynchronous on the context stream"""
+        self._check(self.lib.gsk_sgs_sample_device(self._h, int(nreal), C.c_void_p(d_values) if d_values else None,
+                                                   C.c_void_p(d_z), C.c_void_p(d_out)))
 
     def sgs_weights(self):
         """(nneigh, idx, weights, sigma) of the resident plan (``gsk_sgs_weights``)."""

@@ -1056,11 +1056,23 @@ extern "C" GSK_API int gsk_sgs_sample(gsk_ctx *ctx, int n_realizations, const do
   if (!ctx->sgs) return fail(ctx, GSK_ERR_STATE, "gsk_sgs_sample called before gsk_sgs_plan");
   if (n_realizations < 1 || !z || !out) return fail(ctx, GSK_ERR_INVALID, "gsk_sgs_sample: n_realizations >= 1, z and out required");
   GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
-  return gsk_sgs_sample_impl(ctx, n_realizations, values, z, out);
+  return gsk_sgs_sample_impl(ctx, n_realizations, values, z, out, false);
 } catch (const std::bad_alloc &) {
   return fail(ctx, GSK_ERR_NOMEM, "gsk_sgs_sample: out of host memory");
 } catch (const std::exception &e) {
   return fail(ctx, GSK_ERR_STATE, std::string("gsk_sgs_sample: ") + e.what());
+}
+
+extern "C" GSK_API int gsk_sgs_sample_device(gsk_ctx *ctx, int n_realizations, const double *d_values, const double *d_z,
+                                             double *d_out) try {
+  if (!ctx) return GSK_ERR_INVALID;
+  if (!ctx->sgs) return fail(ctx, GSK_ERR_STATE, "gsk_sgs_sample_device called before gsk_sgs_plan");
+  if (n_realizations < 1 || !d_z || !d_out)
+    return fail(ctx, GSK_ERR_INVALID, "gsk_sgs_sample_device: n_realizations >= 1, d_z and d_out required");
+  GSK_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  return gsk_sgs_sample_impl(ctx, n_realizations, d_values, d_z, d_out, true);
+} catch (const std::exception &e) {
+  return fail(ctx, GSK_ERR_STATE, std::string("gsk_sgs_sample_device: ") + e.what());
 }
 
 extern "C" GSK_API int gsk_sgs_weights(gsk_ctx *ctx, int32_t *nneigh_out, int32_t *neigh_idx_out, double *weights_out,

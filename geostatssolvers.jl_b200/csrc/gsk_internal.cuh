@@ -237,7 +237,7 @@ int gsk_points_unscatter(gsk_ctx *ctx, const int *perm, long long count, const d
 // sgs.cu
 int gsk_sgs_plan_impl(gsk_ctx *ctx, int dim, long long n, const double *const *coords, const long long *rank,
                       const GskVario &vg, double mean, int min_neighbors, int k, double ball_radius);
-int gsk_sgs_sample_impl(gsk_ctx *ctx, int nreal, const double *values, const double *z, double *out);
+int gsk_sgs_sample_impl(gsk_ctx *ctx, int nreal, const double *values, const double *z, double *out, bool on_device);
 int gsk_sgs_weights_impl(gsk_ctx *ctx, int *nn_out, int *nbr_out, double *lam_out, double *sig_out);
 void gsk_sgs_free(gsk_ctx *ctx);
 // peak.cu

@@ -149,7 +149,7 @@ __global__ void sgs_init_kernel(const double *__restrict__ vals, const int *__re
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * nreal) return;
   const long long loc = i % n;
-  out[i] = isdata[loc] ? vals[loc] : nan("");
+  out[i] = isdata[loc] ? (vals ? vals[loc] : 0.0) : nan("");
 }
 
 // One warp per realisation walks the path. The neighbour lists, weights, σ and the draw of position p + 1 are loaded
@@ -459,11 +459,56 @@ int gsk_sgs_plan_impl(gsk_ctx *ctx, int dim, long long n, const double *const *c
   return GSK_OK;
 }
 
-int gsk_sgs_sample_impl(gsk_ctx *ctx, int nreal, const double *values, const double *z, double *out) {
+// the kernels of one gsk_sgs_sample call on device buffers (vals may be nullptr when the plan has no data locations)
+static int sgs_launch(gsk_ctx *ctx, int nreal, const double *d_vals, const double *d_z, double *d_out, int *launches_out) {
+  SgsPlan *s = ctx->sgs;
+  cudaStream_t st = ctx->stream;
+  const size_t n = (size_t)s->n;
+  const long long tot = (long long)n * nreal;
+  sgs_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(d_vals, s->isdata, s->n, nreal, d_out);
+  int launches = 1;
+  if (s->depth > 0) {
+    for (const SgsPlan::Seg &g : s->segs) {
+      if (g.wide) {
+        const int pos0 = s->h_lv_start[(size_t)g.l0], cnt = s->h_lv_start[(size_t)g.l1] - pos0;
+        // realisations in chunks of 65535 (gridDim.y)
+        for (int r0 = 0; r0 < nreal; r0 += 65535) {
+          const dim3 grid((unsigned)((cnt + 127) / 128), (unsigned)std::min(nreal - r0, 65535));
+          sgs_level_kernel<<<grid, 128, 0, st>>>(pos0, cnt, s->m, s->n, s->lv_loc, s->lv_nn, s->lv_nbr, s->lv_lam, s->lv_sig,
+                                                 d_z + (size_t)r0 * n, s->mean, d_out + (size_t)r0 * n);
+          ++launches;
+        }
+      } else {
+        sgs_run_kernel<<<(unsigned)nreal, 256, 0, st>>>(g.l0, g.l1, s->lv_start, s->m, s->n, s->lv_loc, s->lv_nn, s->lv_nbr,
+                                                        s->lv_lam, s->lv_sig, d_z, s->mean, d_out);
+        ++launches;
+      }
+    }
+  } else {
+    sgs_recurrence_kernel<<<(unsigned)nreal, 32, 0, st>>>(s->order, s->m, s->n, s->k, s->nn, s->nbr, s->lam, s->sig, d_z,
+                                                          s->mean, d_out);
+    ++launches;
+  }
+  GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  *launches_out = launches;
+  return GSK_OK;
+}
+
+int gsk_sgs_sample_impl(gsk_ctx *ctx, int nreal, const double *values, const double *z, double *out, bool on_device) {
   SgsPlan *s = ctx->sgs;
   cudaStream_t st = ctx->stream;
   const std::chrono::steady_clock::time_point t_begin = std::chrono::steady_clock::now();
   const size_t n = (size_t)s->n;
+  int launches = 0, rc;
+  if (on_device) {  // the caller's device buffers, asynchronous on the context stream (as gsk_execute)
+    if (!values && s->m < s->n) { ctx->err = "gsk_sgs_sample_device: the plan has data locations, d_values is required"; return GSK_ERR_INVALID; }
+    if ((rc = sgs_launch(ctx, nreal, values, z, out, &launches)) != GSK_OK) return rc;
+    ctx->timing = gsk_timing{};
+    ctx->timing_pending = false;
+    ctx->timing.targets = (long long)s->m * nreal;
+    ctx->timing.launches = launches;
+    return GSK_OK;
+  }
   if (s->cap_real < (size_t)nreal) {
     cudaFree(s->z); cudaFree(s->out); cudaFree(s->vals);
     s->z = s->out = s->vals = nullptr;
@@ -476,33 +521,8 @@ int gsk_sgs_sample_impl(gsk_ctx *ctx, int nreal, const double *values, const dou
   if (values) GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(s->vals, values, sizeof(double) * n, cudaMemcpyHostToDevice, st));
   else GSK_CUDA_CHECK(ctx, cudaMemsetAsync(s->vals, 0, sizeof(double) * n, st));
   GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(s->z, z, sizeof(double) * n * nreal, cudaMemcpyHostToDevice, st));
-  const long long tot = (long long)n * nreal;
   cudaEventRecord(ctx->ev[3], st);
-  sgs_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(s->vals, s->isdata, s->n, nreal, s->out);
-  int launches = 1;
-  if (s->depth > 0) {
-    for (const SgsPlan::Seg &g : s->segs) {
-      if (g.wide) {
-        const int pos0 = s->h_lv_start[(size_t)g.l0], cnt = s->h_lv_start[(size_t)g.l1] - pos0;
-        // realisations in chunks of 65535 (gridDim.y)
-        for (int r0 = 0; r0 < nreal; r0 += 65535) {
-          const dim3 grid((unsigned)((cnt + 127) / 128), (unsigned)std::min(nreal - r0, 65535));
-          sgs_level_kernel<<<grid, 128, 0, st>>>(pos0, cnt, s->m, s->n, s->lv_loc, s->lv_nn, s->lv_nbr, s->lv_lam, s->lv_sig,
-                                                 s->z + (size_t)r0 * n, s->mean, s->out + (size_t)r0 * n);
-          ++launches;
-        }
-      } else {
-        sgs_run_kernel<<<(unsigned)nreal, 256, 0, st>>>(g.l0, g.l1, s->lv_start, s->m, s->n, s->lv_loc, s->lv_nn, s->lv_nbr,
-                                                        s->lv_lam, s->lv_sig, s->z, s->mean, s->out);
-        ++launches;
-      }
-    }
-  } else {
-    sgs_recurrence_kernel<<<(unsigned)nreal, 32, 0, st>>>(s->order, s->m, s->n, s->k, s->nn, s->nbr, s->lam, s->sig, s->z,
-                                                          s->mean, s->out);
-    ++launches;
-  }
-  GSK_CUDA_CHECK(ctx, cudaGetLastError());
+  if ((rc = sgs_launch(ctx, nreal, s->vals, s->z, s->out, &launches)) != GSK_OK) return rc;
   cudaEventRecord(ctx->ev[4], st);
   GSK_CUDA_CHECK(ctx, cudaMemcpyAsync(out, s->out, sizeof(double) * n * nreal, cudaMemcpyDeviceToHost, st));
   GSK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));

@@ -385,13 +385,31 @@ def sgs_draws(pre: dict, rng: np.random.Generator, nreals: int) -> np.ndarray:
     return z
 
 
-def solve_sgs(problem: SimulationProblem, solver: SGS, ctx: Optional[_abi.Context] = None, z: Optional[np.ndarray] = None):
+def solve_sgs(problem: SimulationProblem, solver: SGS, ctx: Optional[_abi.Context] = None, z: Optional[np.ndarray] = None,
+              device_draws: bool = False):
     """``solve(problem, SGS(...))`` for one variable — a list of `nreals` GeoTables. `z` (nreals × nelements) overrides
-    the draws (parity tests hand the oracle the same numbers)."""
+    the draws (parity tests hand the oracle the same numbers). `device_draws=True` draws on the GPU (torch.randn with a
+    generator seeded from `solver.rng`) and samples on device buffers (gsk_sgs_sample_device): only the realisations
+    cross PCIe, once, through pinned memory."""
     ctx = ctx or default_context()
     var = problem.variables()[0]
     pre = preprocess_sgs(problem, solver, var, ctx)
     nreals = problem.nreals()
+    if device_draws and z is None:
+        import torch
+        dev = torch.device("cuda", ctx.device)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(solver.rng.integers(0, 2 ** 62)))
+        dz = torch.randn((nreals, pre["npts"]), dtype=torch.float64, device=dev, generator=gen)
+        dvals = torch.from_numpy(pre["values"]).to(dev)
+        dout = torch.empty_like(dz)
+        torch.cuda.synchronize(dev)
+        ctx.sgs_sample_device(nreals, dvals.data_ptr(), dz.data_ptr(), dout.data_ptr())
+        ctx.synchronize()
+        host = torch.empty(dout.shape, dtype=torch.float64, pin_memory=True)
+        host.copy_(dout)
+        reals = host.numpy()
+        return [georef({var: reals[r]}, problem.domain()) for r in range(nreals)]
     if z is None:
         z = sgs_draws(pre, solver.rng, nreals)
     reals = ctx.sgs_sample(np.asarray(z, dtype=np.float64).reshape(nreals, pre["npts"]), values=pre["values"])

@@ -247,6 +247,10 @@ GSK_API int gsk_sgs_plan(gsk_ctx *ctx, int dim, int64_t n, const double *const *
  * out (n_realizations × n): the data values, and for the others mean + Σ_j λ_ij (out[n_ij] − mean) + σ_i z_i — or
  * mean + √sill·z_i where fewer than min_neighbors were found or the factorisation failed (seq.jl:108-110,126-128). */
 GSK_API int gsk_sgs_sample(gsk_ctx *ctx, int n_realizations, const double *values, const double *z, double *out);
+/* the same on DEVICE buffers (d_values may be NULL when no element holds data), asynchronous on the context stream like
+ * gsk_execute: for callers that draw on the GPU, nothing crosses PCIe */
+GSK_API int gsk_sgs_sample_device(gsk_ctx *ctx, int n_realizations, const double *d_values, const double *d_z,
+                                  double *d_out);
 /* the plan's per-element neighbour counts (n), neighbour indices (n × k, -1 padded; k = min(max_neighbors, n)),
  * weights (n × k) and conditional standard deviations (n); any pointer may be NULL */
 GSK_API int gsk_sgs_weights(gsk_ctx *ctx, int32_t *nneigh_out, int32_t *neigh_idx_out, double *weights_out,

@@ -166,3 +166,38 @@ def test_sgs_ar1_known_answer(gsk, ctx):
     for i in range(1, n):
         want[i] = mu + rho * (want[i - 1] - mu) + np.sqrt(s * (1.0 - rho * rho)) * z[i]
     np.testing.assert_allclose(out, want, rtol=1e-10, atol=1e-10)
+
+
+def test_sgs_device_buffers(gsk, ctx):
+    """gsk_sgs_sample_device on the caller's device buffers gives the bytes of the host-buffer call; solve() with
+    device_draws honours the data"""
+    import torch
+    dims = (50, 40)
+    n = dims[0] * dims[1]
+    coords = _grid_coords(dims)
+    rng = np.random.default_rng(2)
+    data_idx = rng.choice(n, 9, replace=False)
+    rank = _rank(n, data_idx, rng.permutation(n))
+    values = np.zeros(n)
+    values[data_idx] = rng.standard_normal(9)
+    z = rng.standard_normal((5, n))
+    ctx.sgs_plan(coords, rank, vario_kind=gsk.VARIO_EXPONENTIAL, vario_range=9.0, max_neighbors=12)
+    want = ctx.sgs_sample(z, values=values)
+    dz = torch.from_numpy(z).cuda()
+    dv = torch.from_numpy(values).cuda()
+    dout = torch.empty_like(dz)
+    torch.cuda.synchronize()
+    ctx.sgs_sample_device(5, dv.data_ptr(), dz.data_ptr(), dout.data_ptr())
+    ctx.synchronize()
+    assert np.array_equal(dout.cpu().numpy(), want)
+    with pytest.raises(gsk.GskError):
+        ctx.sgs_sample_device(5, 0, dz.data_ptr(), dout.data_ptr())   # the plan has data: values are required
+    from gskrige import simulation as sim
+    S = gsk.georef({"z": [1.0, 0.0, 1.0]}, np.array([[25.0, 50.0, 75.0], [25.0, 75.0, 50.0]]))
+    D = gsk.CartesianGrid((100, 100), (0.5, 0.5), (1.0, 1.0))
+    solver = gsk.SGS(z=dict(variogram=gsk.SphericalVariogram(range=35.0), path=gsk.RandomPath(1)), rng=3)
+    sol = sim.solve_sgs(gsk.SimulationProblem(S, D, "z", 4), solver, ctx, device_draws=True)
+    for t in sol:
+        col = np.asarray(t["z"])
+        assert col[24 * 100 + 24] == 1.0 and col[74 * 100 + 49] == 0.0 and col[49 * 100 + 74] == 1.0
+        assert np.isfinite(col).all() and 0.3 < col.std() < 3.0
