@@ -116,6 +116,12 @@ struct GskSearchArgs {
   int *nn;         // out: neighbours per target
   int *nbr;        // out: count × k original indices sorted by (d², idx), −1 padded
   const int *trank;  // ranked search (sgs.cu) only: rank + 1 of every target; records carry theirs in the high half of w
+  // compact-key pass (search.cu): the low `keybits` bits of a list entry hold the sample index; tiles whose result
+  // may depend on the dropped distance bits are appended to redo_list (redo_count of them) and searched again by
+  // the exact-key variant, launched with redo_list set
+  int keybits;
+  int *redo_list;
+  int *redo_count;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -129,7 +135,7 @@ struct SgsPlan;     // sgs.cu
 enum GskBufId {
   BUF_REC_ORIG, BUF_REC_SORTED, BUF_CELL_START, BUF_SUP, BUF_PTS0, BUF_PTS1, BUF_PTS2, BUF_CELL_OF, BUF_COUNTS,
   BUF_G_A, BUF_G_X, BUF_G_DINV, BUF_G_E, BUF_G_YE, BUF_G_GEE, BUF_G_BM, BUF_G_PARTIAL, BUF_G_W, BUF_G_TMP, BUF_G_DMEAN, BUF_PEAK,
-  BUF_PT_CELL, BUF_PT_COUNTS, BUF_PT_PERM, BUF_PT_X, BUF_PT_Y, BUF_PT_Z, BUF_PT_MEAN, BUF_PT_VAR, BUF_PT_NN, BUF_PT_NBR, BUF_VALS, BUF_COUNT
+  BUF_PT_CELL, BUF_PT_COUNTS, BUF_PT_PERM, BUF_PT_X, BUF_PT_Y, BUF_PT_Z, BUF_PT_MEAN, BUF_PT_VAR, BUF_PT_NN, BUF_PT_NBR, BUF_VALS, BUF_REDO, BUF_COUNT
 };
 
 struct gsk_ctx {

@@ -89,15 +89,34 @@ __device__ __forceinline__ int block_excl_scan(int v, int *warp_buf, int *total)
 // RANKED (sequential simulation, sgs.cu): records carry a rank in the high 32 bits of w next to the index, the target
 // its own rank, and only records of LOWER rank are candidates — the `mask = simulated` of the reference's sequential
 // loop (ref: src/simulation/seq.jl:105), evaluated for every location of the path at once.
-template <int TX, int TY, int TZ, int DIM, bool HEAP, bool RANKED = false>
+//
+// CK (compact keys): a list entry is ONE 64-bit word — the bits of d² with the low `keybits` mantissa bits replaced by
+// the sample index (n <= 2^keybits) — so the (d², index) order is a single unsigned compare, the list takes 8 instead
+// of 12 bytes per entry (more resident CTAs: the kernel is latency-bound) and tied distances still fall to the lower
+// index. Two candidates whose d² differ only in the dropped bits would be ordered by index instead: a thread that
+// meets such a pair where it matters (inside its final list, or between its k-th best and a rejected/evicted
+// candidate) flags its tile, and the tile is searched again by the exact-key variant (redo list, same stream), so the
+// result is the exact (d², index) order in every case. Distances whose dropped bits are all zero (lattice data) lose
+// nothing and never flag.
+template <int TX, int TY, int TZ, int DIM, bool HEAP, bool RANKED = false, bool CK = false>
 __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
   static_assert(TX * TY * TZ == NT, "tile must hold NT targets");
+  static_assert(!(CK && RANKED), "ranked search keeps exact keys");
+  typedef unsigned long long u64;
+  // redo pass (exact keys): CTA i searches the i-th tile flagged by the compact-key pass
+  int tile_id = blockIdx.x;
+  if (!CK && a.redo_list) {
+    if (blockIdx.x >= (unsigned)*a.redo_count) return;
+    tile_id = a.redo_list[blockIdx.x];
+  }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = a.k;
   const int SCAP = a.scap;
   double4 *stage = reinterpret_cast<double4 *>(smem_raw);                 // SCAP records
   double *topd = reinterpret_cast<double *>(smem_raw + sizeof(double4) * SCAP);  // [K][NT]
   int *topi = reinterpret_cast<int *>(topd + (size_t)K * NT);             // [K][NT]
+  u64 *topk = reinterpret_cast<u64 *>(topd);                               // CK: [K][NT] keys instead
+  const u64 LOWMASK = CK ? ((1ull << a.keybits) - 1ull) : 0ull;
   __shared__ uint64_t bar;
   __shared__ int warp_buf[NT / 32];
   __shared__ int sh_bb[6];
@@ -114,7 +133,7 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
   int my_rank = 0;  // RANKED only
   int b0[3] = {0, 0, 0}, b1[3] = {0, 0, 0};  // bins overlapped by the tile's targets
   if (tg.is_grid) {
-    int tile = blockIdx.x;
+    int tile = tile_id;
     int tix = tile % a.ntile[0];
     int tiy = (tile / a.ntile[0]) % a.ntile[1];
     int tiz = tile / (a.ntile[0] * a.ntile[1]);
@@ -142,7 +161,7 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
       }
     }
   } else {
-    long long t = (long long)blockIdx.x * NT + tid;
+    long long t = (long long)tile_id * NT + tid;
     active = t < a.count;
     lin = a.first + t;
     int mb[3] = {0, 0, 0};
@@ -177,8 +196,11 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
   uint32_t parity = 0;
 
   int cnt = 0;
-  double worst = INFINITY;  // k-th best d² once the list is full
+  double worst = INFINITY;  // k-th best d² once the list is full (CK: the largest d² that shares its key's distance bits)
   int worst_i = 0x7fffffff;
+  u64 wkey = ~0ull;         // CK: key of the k-th best
+  u64 lowbits = 0ull;       // CK: OR of the d² bits of every candidate that was not rejected on distance alone
+  u64 amb = ~0ull;          // CK: distance bits at which the last candidate tied with the k-th best was left out
   const double r2 = a.use_ball ? a.radius * a.radius : INFINITY;
   // slack that keeps the "strictly inside the scanned block" test conservative against the
   // rounding of the bin assignment
@@ -257,14 +279,93 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
             }
             return d2;
           };
+#define TD(sl) topd[(size_t)(sl) * NT + tid]
+#define TI(sl) topi[(size_t)(sl) * NT + tid]
+#define TK(sl) topk[(size_t)(sl) * NT + tid]
           auto consider = [&](const double d2, const double w) {
             if (d2 > worst) return;
             const long long wl = __double_as_longlong(w);
             if (RANKED && (int)(wl >> 32) >= my_rank) return;
             const int oi = (int)wl;
+            if (CK) {
+              const u64 bits = (u64)__double_as_longlong(d2);
+              const u64 kc = (bits & ~LOWMASK) | (u64)(unsigned)oi;
+              lowbits |= bits;
+              if (cnt == K) {
+                if (kc > wkey) {  // same distance bits as the k-th best (it passed the distance test), sorted behind it
+                  amb = wkey & ~LOWMASK;
+                  return;
+                }
+              }
+              if (!HEAP) {
+                // ascending list, sorted insertion from the tail; a full list drops its last entry
+                const int p0 = (cnt < K) ? cnt : K - 1;
+                u64 *pk = &TK(p0);
+                u64 *const pk_first = &TK(0);
+                while (pk != pk_first) {
+                  const u64 kp = pk[-NT];
+                  if (kc > kp) break;
+                  pk[0] = kp;
+                  pk -= NT;
+                }
+                pk[0] = kc;
+                if (cnt < K) {
+                  if (++cnt == K) {
+                    wkey = TK(K - 1);
+                    worst = __longlong_as_double((long long)(wkey | LOWMASK));
+                  }
+                } else {
+                  const u64 nw = TK(K - 1);
+                  if (((nw ^ wkey) & ~LOWMASK) == 0ull) amb = nw & ~LOWMASK;  // the dropped entry ties with the new k-th
+                  wkey = nw;
+                  worst = __longlong_as_double((long long)(wkey | LOWMASK));
+                }
+              } else {
+                int i;
+                if (cnt < K) {  // sift up
+                  i = cnt++;
+                  while (i > 0) {
+                    const int par = (i - 1) >> 1;
+                    const u64 kp = TK(par);
+                    if (kc > kp) {
+                      TK(i) = kp;
+                      i = par;
+                    } else {
+                      break;
+                    }
+                  }
+                  TK(i) = kc;
+                  if (cnt == K) {
+                    wkey = TK(0);
+                    worst = __longlong_as_double((long long)(wkey | LOWMASK));
+                  }
+                } else {  // replace the root (the current k-th best), sift down
+                  i = 0;
+                  for (;;) {
+                    int c = 2 * i + 1;
+                    if (c >= K) break;
+                    u64 kch = TK(c);
+                    if (c + 1 < K) {
+                      const u64 kr = TK(c + 1);
+                      if (kr > kch) { kch = kr; ++c; }
+                    }
+                    if (kch > kc) {
+                      TK(i) = kch;
+                      i = c;
+                    } else {
+                      break;
+                    }
+                  }
+                  TK(i) = kc;
+                  const u64 nw = TK(0);
+                  if (((nw ^ wkey) & ~LOWMASK) == 0ull) amb = nw & ~LOWMASK;  // the evicted entry ties with the new k-th
+                  wkey = nw;
+                  worst = __longlong_as_double((long long)(wkey | LOWMASK));
+                }
+              }
+              return;
+            }
             if (d2 == worst && oi > worst_i) return;
-#define TD(sl) topd[(size_t)(sl) * NT + tid]
-#define TI(sl) topi[(size_t)(sl) * NT + tid]
             if (!HEAP) {
               // sorted insertion with running pointers (slot stride NT is a compile-time constant, so the
               // neighbouring slot is an immediate offset) and a branch-free (d², index) comparison
@@ -391,6 +492,49 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
   }
 
   // ---- emit: ascending (d², idx); ball search keeps sqrt(d²) <= radius (inclusive) ----
+  if (CK) {
+    bool flag = false;
+    if (active) {
+      if (HEAP) {  // heap sort in place on the keys
+        for (int end = cnt - 1; end > 0; --end) {
+          const u64 kk = TK(end);
+          TK(end) = TK(0);
+          int i = 0;
+          for (;;) {
+            int c = 2 * i + 1;
+            if (c >= end) break;
+            u64 kch = TK(c);
+            if (c + 1 < end) {
+              const u64 kr = TK(c + 1);
+              if (kr > kch) { kch = kr; ++c; }
+            }
+            if (kch > kk) {
+              TK(i) = kch;
+              i = c;
+            } else {
+              break;
+            }
+          }
+          TK(i) = kk;
+        }
+      }
+      const long long t = lin - a.first;
+      a.nn[t] = cnt;
+      int *out = a.nbr + t * K;
+      u64 prev = ~0ull;
+      bool tie = false;
+      for (int i = 0; i < K; ++i) {
+        const u64 kk = (i < cnt) ? TK(i) : ~0ull;
+        tie = tie || (((kk ^ prev) & ~LOWMASK) == 0ull && i < cnt);
+        prev = kk;
+        out[i] = (i < cnt) ? (int)(kk & LOWMASK) : -1;
+      }
+      // dropped distance bits only matter when some candidate had any
+      if ((lowbits & LOWMASK) != 0ull) flag = tie || (cnt == K && amb == (wkey & ~LOWMASK));
+    }
+    if (__syncthreads_or(flag ? 1 : 0) && tid == 0) a.redo_list[atomicAdd(a.redo_count, 1)] = tile_id;
+    return;
+  }
   if (active) {
     if (HEAP) {  // heap sort in place: repeatedly move the maximum behind the shrinking heap
       for (int end = cnt - 1; end > 0; --end) {
@@ -433,6 +577,7 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
   }
 #undef TD
 #undef TI
+#undef TK
 }
 
 }  // namespace
@@ -451,11 +596,11 @@ int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long 
   a.nn = d_nn;
   a.nbr = d_nbr;
   for (int d = 0; d < 3; ++d) a.margin0[d] = ctx->margin0[d];
+  static const int scap_env = GSK_DEV_ENV("GSK_SCAP") ? atoi(GSK_DEV_ENV("GSK_SCAP")) : 0;
   {
     // staging capacity: just enough for the block a tile is expected to scan (smaller shared-memory footprint
     // → more resident CTAs, which is what the latency-bound insertion loop needs); larger blocks are simply
     // processed in several chunks. GSK_SCAP overrides (development tunable).
-    static const int scap_env = GSK_DEV_ENV("GSK_SCAP") ? atoi(GSK_DEV_ENV("GSK_SCAP")) : 0;
     double expect = 512.0;
     const int dim = ctx->tg.dim;
     if (ctx->tg.is_grid && ctx->bins.ncells > 0) {
@@ -470,7 +615,6 @@ int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long 
     while (sc < SCAP_MAX && sc < 1.25 * expect) sc *= 2;
     a.scap = scap_env > 0 ? std::min(scap_env, SCAP_MAX) : sc;
   }
-  const size_t smem = sizeof(double4) * a.scap + (size_t)a.k * NT * (sizeof(double) + sizeof(int));
   const int dim = ctx->tg.dim;
   unsigned nblocks;
   int tile[3] = {NT, 1, 1};
@@ -501,13 +645,46 @@ int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long 
   } else {
     nblocks = (unsigned)((count + NT - 1) / NT);
   }
+  // compact keys (8 bytes per list entry) whenever the sample index fits beside >= 28 bits of the distance's mantissa;
+  // ball searches (which need sqrt of the exact d²) and ranked searches keep exact keys
+  int keybits = 1;
+  while (keybits < 31 && (1ll << keybits) < ctx->prob.n_samples) ++keybits;
+  static const int no_ck = GSK_DEV_ENV("GSK_NO_COMPACT_KEYS") ? atoi(GSK_DEV_ENV("GSK_NO_COMPACT_KEYS")) : 0;  // development tunable
+  const bool ck = !d_trank && !a.use_ball && keybits <= 24 && !no_ck;
+  a.keybits = keybits;
+  if (ck) {
+    void *p = nullptr;
+    int rc = gsk_buf(ctx, BUF_REDO, sizeof(int) * ((size_t)nblocks + 1), &p);
+    if (rc != GSK_OK) return rc;
+    a.redo_count = reinterpret_cast<int *>(p);
+    a.redo_list = a.redo_count + 1;
+    GSK_CUDA_CHECK(ctx, cudaMemsetAsync(a.redo_count, 0, sizeof(int), st));
+    if (scap_env <= 0) {
+      // the smaller list leaves room for more CTAs: shrink the stage while that adds another resident CTA (measured,
+      // C3a k = 32: 512 records 2.07 ms, 256 1.81 ms, 128 1.66 ms per 2M targets; C5 k = 64: 512 6.36 ms, 256 = 128 4.7 ms)
+      auto ctas = [&](int sc) { return (int)(232448 / (sizeof(double4) * sc + (size_t)a.k * NT * 8 + 1024 + 64)); };
+      while (a.scap > 128 && ctas(a.scap / 2) > ctas(a.scap)) a.scap /= 2;
+    }
+  }
+  const size_t smem_exact = sizeof(double4) * a.scap + (size_t)a.k * NT * (sizeof(double) + sizeof(int));
+  const size_t smem = ck ? sizeof(double4) * a.scap + (size_t)a.k * NT * sizeof(unsigned long long) : smem_exact;
   cudaError_t e;
   static const int heap_min_k = GSK_DEV_ENV("GSK_HEAP_MIN_K") ? atoi(GSK_DEV_ENV("GSK_HEAP_MIN_K")) : 24;  // development tunable
   const bool heap = a.k >= heap_min_k;
 #define GSK_LAUNCH_SEARCH(TX, TY, TZ, D, H)                                                                        \
   do {                                                                                                             \
-    e = cudaFuncSetAttribute(search_kernel<TX, TY, TZ, D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e == cudaSuccess) search_kernel<TX, TY, TZ, D, H><<<nblocks, NT, smem, st>>>(a);                           \
+    if (ck) {                                                                                                      \
+      e = cudaFuncSetAttribute(search_kernel<TX, TY, TZ, D, H, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e == cudaSuccess) search_kernel<TX, TY, TZ, D, H, false, true><<<nblocks, NT, smem, st>>>(a);            \
+      if (e == cudaSuccess) e = cudaGetLastError();                                                                \
+    } else {                                                                                                       \
+      a.redo_list = nullptr;                                                                                       \
+      a.redo_count = nullptr;                                                                                      \
+      e = cudaSuccess;                                                                                             \
+    }                                                                                                              \
+    if (e == cudaSuccess)                                                                                          \
+      e = cudaFuncSetAttribute(search_kernel<TX, TY, TZ, D, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_exact); \
+    if (e == cudaSuccess) search_kernel<TX, TY, TZ, D, H><<<nblocks, NT, smem_exact, st>>>(a);                     \
   } while (0)
 #define GSK_LAUNCH_RANKED(D, H)                                                                                    \
   do {                                                                                                             \
@@ -530,6 +707,6 @@ int gsk_launch_search(gsk_ctx *ctx, cudaStream_t st, long long first, long long 
 #undef GSK_LAUNCH_RANKED
   GSK_CUDA_CHECK(ctx, e);
   GSK_CUDA_CHECK(ctx, cudaGetLastError());
-  if (launches) *launches += 1;
+  if (launches) *launches += ck ? 2 : 1;
   return GSK_OK;
 }
