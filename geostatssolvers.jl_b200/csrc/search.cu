@@ -98,8 +98,11 @@ __device__ __forceinline__ int block_excl_scan(int v, int *warp_buf, int *total)
 // candidate) flags its tile, and the tile is searched again by the exact-key variant (redo list, same stream), so the
 // result is the exact (d², index) order in every case. Distances whose dropped bits are all zero (lattice data) lose
 // nothing and never flag.
+// Launch bounds: the heap variants are asked for six CTAs per SM (<= 80 registers): left alone the compiler picks 56
+// registers and spills into the hot loop (C5 search 4.60 -> 4.49 ms per 2M targets without the spills); the insertion
+// variants stay at 72 registers (seven CTAs; at 80 the C2 search goes from 0.271 to 0.291 ms).
 template <int TX, int TY, int TZ, int DIM, bool HEAP, bool RANKED = false, bool CK = false>
-__global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
+__global__ void __launch_bounds__(NT, HEAP ? 6 : 7) search_kernel(const GskSearchArgs a) {
   static_assert(TX * TY * TZ == NT, "tile must hold NT targets");
   static_assert(!(CK && RANKED), "ranked search keeps exact keys");
   typedef unsigned long long u64;
@@ -282,6 +285,25 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
 #define TD(sl) topd[(size_t)(sl) * NT + tid]
 #define TI(sl) topi[(size_t)(sl) * NT + tid]
 #define TK(sl) topk[(size_t)(sl) * NT + tid]
+          // CK max-heap: put `key` into the hole at slot i of a heap of n keys, moving larger children up
+          auto ck_sift_down = [&](int i, const int n, const u64 key) {
+            for (;;) {
+              int c = 2 * i + 1;
+              if (c >= n) break;
+              u64 kch = TK(c);
+              if (c + 1 < n) {
+                const u64 kr = TK(c + 1);
+                if (kr > kch) { kch = kr; ++c; }
+              }
+              if (kch > key) {
+                TK(i) = kch;
+                i = c;
+              } else {
+                break;
+              }
+            }
+            TK(i) = key;
+          };
           auto consider = [&](const double d2, const double w) {
             if (d2 > worst) return;
             const long long wl = __double_as_longlong(w);
@@ -321,42 +343,18 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
                   worst = __longlong_as_double((long long)(wkey | LOWMASK));
                 }
               } else {
-                int i;
-                if (cnt < K) {  // sift up
-                  i = cnt++;
-                  while (i > 0) {
-                    const int par = (i - 1) >> 1;
-                    const u64 kp = TK(par);
-                    if (kc > kp) {
-                      TK(i) = kp;
-                      i = par;
-                    } else {
-                      break;
-                    }
-                  }
-                  TK(i) = kc;
-                  if (cnt == K) {
+                if (cnt < K) {
+                  // The first K candidates are only appended; the heap is built once the list is full (Floyd: at most
+                  // K level steps in total). Candidates arrive roughly nearest first, so sifting each one up a
+                  // max-heap would climb to the root every time (log2(cnt) levels each).
+                  TK(cnt) = kc;
+                  if (++cnt == K) {
+                    for (int i = K / 2 - 1; i >= 0; --i) ck_sift_down(i, K, TK(i));
                     wkey = TK(0);
                     worst = __longlong_as_double((long long)(wkey | LOWMASK));
                   }
-                } else {  // replace the root (the current k-th best), sift down
-                  i = 0;
-                  for (;;) {
-                    int c = 2 * i + 1;
-                    if (c >= K) break;
-                    u64 kch = TK(c);
-                    if (c + 1 < K) {
-                      const u64 kr = TK(c + 1);
-                      if (kr > kch) { kch = kr; ++c; }
-                    }
-                    if (kch > kc) {
-                      TK(i) = kch;
-                      i = c;
-                    } else {
-                      break;
-                    }
-                  }
-                  TK(i) = kc;
+                } else {  // replace the root (the current k-th best)
+                  ck_sift_down(0, K, kc);
                   const u64 nw = TK(0);
                   if (((nw ^ wkey) & ~LOWMASK) == 0ull) amb = nw & ~LOWMASK;  // the evicted entry ties with the new k-th
                   wkey = nw;
@@ -495,27 +493,31 @@ __global__ void __launch_bounds__(NT) search_kernel(const GskSearchArgs a) {
   if (CK) {
     bool flag = false;
     if (active) {
-      if (HEAP) {  // heap sort in place on the keys
-        for (int end = cnt - 1; end > 0; --end) {
-          const u64 kk = TK(end);
-          TK(end) = TK(0);
-          int i = 0;
+      if (HEAP) {  // heap sort in place on the keys (a list that never filled up is still unordered: build its heap first)
+        auto sift_down = [&](int i, const int n, const u64 key) {
           for (;;) {
             int c = 2 * i + 1;
-            if (c >= end) break;
+            if (c >= n) break;
             u64 kch = TK(c);
-            if (c + 1 < end) {
+            if (c + 1 < n) {
               const u64 kr = TK(c + 1);
               if (kr > kch) { kch = kr; ++c; }
             }
-            if (kch > kk) {
+            if (kch > key) {
               TK(i) = kch;
               i = c;
             } else {
               break;
             }
           }
-          TK(i) = kk;
+          TK(i) = key;
+        };
+        if (cnt < K)
+          for (int i = cnt / 2 - 1; i >= 0; --i) sift_down(i, cnt, TK(i));
+        for (int end = cnt - 1; end > 0; --end) {
+          const u64 kk = TK(end);
+          TK(end) = TK(0);
+          sift_down(0, end, kk);
         }
       }
       const long long t = lin - a.first;

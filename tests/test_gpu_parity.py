@@ -223,6 +223,52 @@ def test_ties_fall_to_lower_index(gsk, ctx, oracle):
     assert np.array_equal(idx, oidx)
 
 
+@pytest.mark.parametrize("dim,k", [(2, 6), (2, 30), (3, 12), (3, 40)])
+def test_ties_on_a_non_dyadic_lattice(gsk, ctx, oracle, dim, k):
+    """Lattice coordinates that are not exactly representable (multiples of 0.3): mathematically tied distances come
+    out of the rounding chain equal or a few ulps apart. The search keeps 64-bit keys (distance bits + sample index)
+    that drop the low mantissa bits; every tile where those bits could matter must come back from the exact redo
+    pass, so the lists still equal the oracle's (d², index) order bit for bit."""
+    ax = np.arange(12) * 0.3
+    g = np.meshgrid(*([ax] * dim), indexing="ij")
+    coords = [c.ravel().copy() for c in g]
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(len(coords[0]))           # index order unrelated to position
+    coords = [c[perm] for c in coords]
+    vals = np.cos(coords[0] * 3.0) + 0.1 * coords[-1]
+    spec = gsk.ProblemSpec(coords=coords, values=vals, grid_dims=(36,) * dim, grid_origin=(-0.05,) * dim,
+                           grid_spacing=(0.1,) * dim, vario_kind=gsk.VARIO_SPHERICAL, vario_range=2.0,
+                           max_neighbors=k)
+    (mean, var, nn, idx), (om, ov, onn, oidx) = _both(ctx, oracle, spec, oracle.SEARCH_BRUTE)
+    assert np.array_equal(nn, onn) and np.array_equal(idx, oidx)
+
+
+@pytest.mark.parametrize("k", [3, 4, 24, 25])
+def test_distances_that_differ_only_in_the_dropped_key_bits(gsk, ctx, oracle, k):
+    """Pairs of samples placed symmetrically about a column of targets, one of each pair moved outwards by a few ulps
+    and given the LOWER index: ordering by the truncated distance and then by index would put it first, the exact
+    (d², index) order puts it second — also across the k-th / (k+1)-th boundary (k odd cuts a pair)."""
+    rng = np.random.default_rng(9)
+    npair = 16
+    a = 0.37 + 1.13 * np.arange(1, npair + 1)        # half-distances of the pairs, increasing
+    xs, ys = [], []
+    for j in range(npair):
+        far = 50.5 + a[j]
+        far = np.nextafter(np.nextafter(far, np.inf), np.inf)
+        xs += [far, 50.5 - a[j]]                      # lower index: (slightly) farther
+        ys += [50.5, 50.5]
+    filler = rng.uniform(0, 100, (9000, 2))               # n > 2^12: at least 13 dropped bits
+    filler = filler[np.abs(filler[:, 1] - 50.5) > 30.0]   # far from the targets of interest
+    x = np.concatenate([np.array(xs), filler[:, 0]]); y = np.concatenate([np.array(ys), filler[:, 1]])
+    vals = np.sin(x / 7.0) + 0.05 * y
+    spec = gsk.ProblemSpec(coords=[x, y], values=vals, grid_dims=(100, 100), vario_kind=gsk.VARIO_SPHERICAL,
+                           vario_range=40.0, max_neighbors=k)
+    (mean, var, nn, idx), (om, ov, onn, oidx) = _both(ctx, oracle, spec, oracle.SEARCH_BRUTE)
+    assert np.array_equal(nn, onn) and np.array_equal(idx, oidx)
+    row = 50 * 100 + 50                               # the target at (50.5, 50.5): every pair is a near-tie there
+    assert oidx[row, 0] == 1 and oidx[row, 1] == 0    # exact order: the nearer sample (index 1) first
+
+
 # ---- sharding and the resident form ----
 def test_slabs_equal_full(gsk, ctx):
     spec = gsk.synth.config_spec("C3a", scale=0.14)
