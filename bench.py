@@ -382,6 +382,13 @@ class Workload:
                 "ms_per_step": e2e_s * 1e3, "steps": steps,
                 "api": "gsk_krige (C ABI, pinned host buffers; sample upload + bin build / factorisation + kernels + D2H per call)"}
 
+    def launches_per_chunk(self):
+        """Kernels per chunk of <= 2^20 targets on the local path: the compact-key search, its exact redo pass (both
+        launched whenever the sample index fits the key: n <= 2^24 and no ball) and the solve kernel."""
+        p = self.spec.params
+        ball = p["ball_radius"] == p["ball_radius"]
+        return 3 if (self.spec.n_samples <= (1 << 24) and not ball) else 2
+
     def roofline(self, ms_per_step, solve_ms, search_ms, launches, dfma, dmma):
         gsk, spec, k = self.env.gsk, self.spec, self.k
         flops_t = gsk.synth.algorithmic_flops_per_target(spec)
@@ -391,7 +398,7 @@ class Workload:
         if tf.exists():
             per_target = json.loads(tf.read_text()).get("bytes_per_target", {}).get(self.name)
             if per_target is not None and k:
-                traffic = per_target * self.count / max(1, launches // 2)   # per launch, like `achieved`'s launch set / its launches
+                traffic = per_target * self.count / max(1, launches // self.launches_per_chunk())   # per launch, like `achieved`'s launch set / its launches
         extra = {}
         count = self.count
         if k:
@@ -402,7 +409,7 @@ class Workload:
             step_ms = (search_ms + solve_ms) if search_ms else ms_per_step
             extra = {"frac_step": flops_t * count / (step_ms * 1e-3) / 1e12 / dfma,
                      "frac_step_note": "same algorithmic flops over search + solve kernel time (the whole per-target path)"}
-            nlaunch = max(1, launches // 2)
+            nlaunch = max(1, launches // self.launches_per_chunk())
         else:
             # global path: the Gram formulation needs only the forward triangular solve, i.e. n^2 flop per target
             # instead of the canonical 2(n+c)^2 - both are reported; frac uses the EXECUTED flops (conservative)

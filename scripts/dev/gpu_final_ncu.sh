@@ -8,7 +8,7 @@ echo "launch list rc=$?"
 python scripts/ncu_launches.py gpurun_out/final/r02_launches.csv > gpurun_out/final/r02_launch_list_summary.txt
 for cfg in C5:2097152 C3a:2097152 C3b:2097152 C2:0; do
   c=${cfg%%:*}; t=${cfg##*:}; targ=""; [ "$t" != "0" ] && targ="--targets $t"
-  ncu --set full --clock-control none --import-source on -k regex:"search_kernel|local_solve" -c 2 -o /tmp/r02_final_$c -f \
+  ncu --set full --clock-control none --import-source on -k regex:"search_kernel|local_solve" -c 3 -o /tmp/r02_final_$c -f \
     python bench.py --config $c $targ --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/final/r02_final_$c.log 2>&1
   echo "ncu $c rc=$?"
   python scripts/ncu_summary.py /tmp/r02_final_$c.ncu-rep > gpurun_out/final/r02_final_${c}_summary.txt 2>&1
