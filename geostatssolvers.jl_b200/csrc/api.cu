@@ -611,10 +611,13 @@ static int execute_impl(gsk_ctx *ctx, int64_t first, int64_t count, int32_t *d_n
     launches += 4;
   } else {
     const int k = ctx->prob.max_neighbors;
-    // chunks of ~1M targets bound the neighbour-list scratch (4k+4 B per target); chunk edges are aligned
-    // to whole tile layers of the grid where that is cheap. (Running the search of chunk c+1 on a side stream while
-    // chunk c is solved was measured on B200 in round 1: no gain — both kernels already fill the SMs.)
-    long long chunk = 1ll << 20;
+    // chunks of ~4M targets bound the neighbour-list scratch (4k+4 B per target: 1.1 GB at k = 64); chunk edges are aligned
+    // to whole tile layers of the grid where that is cheap. 4M instead of 1M targets per launch: the search kernel's
+    // 8 192 CTAs were 18.4 waves of the 444 resident ones, its last wave ran at half occupancy (C5 search 315 -> 308 ms
+    // per 512^3 grid, C3a 13.6 -> 13.0 ms). (Running the search of chunk c+1 on a side stream while chunk c is solved
+    // was measured on B200 in round 1: no gain — both kernels already fill the SMs.)
+    static const int chunk_log2 = GSK_DEV_ENV("GSK_CHUNK_LOG2") ? atoi(GSK_DEV_ENV("GSK_CHUNK_LOG2")) : 22;  // development tunable
+    long long chunk = 1ll << chunk_log2;
     if (ctx->tg.is_grid) {
       const int dim = ctx->tg.dim;
       long long unit = (dim == 3) ? ctx->tg.gdim[0] * ctx->tg.gdim[1] * 4 : (dim == 2 ? ctx->tg.gdim[0] * 8 : 128);
