@@ -269,6 +269,20 @@ def test_distances_that_differ_only_in_the_dropped_key_bits(gsk, ctx, oracle, k)
     assert oidx[row, 0] == 1 and oidx[row, 1] == 0    # exact order: the nearer sample (index 1) first
 
 
+def test_one_call_over_several_chunks_equals_slab_calls(gsk, ctx):
+    """gsk_execute cuts a range into chunks of ~4M targets (search + solve per chunk, chunk edges on tile layers): a
+    9M-target grid computed in ONE call must equal, bit for bit, the same grid computed slab by slab with slab edges
+    that fall inside chunks and off the tile lattice."""
+    spec = gsk.synth.config_spec("C2", grid=(3000, 3000), n=90_000)
+    T = spec.n_targets
+    mean, var = ctx.krige(spec)
+    assert np.isfinite(mean).all() and np.isfinite(var).all()
+    cuts = [0, 1_234_567, 4_194_304 + 11, 6_000_000, T]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        m, v = ctx.krige(spec.with_slab(a, b - a))
+        assert np.array_equal(m, mean[a:b]) and np.array_equal(v, var[a:b])
+
+
 # ---- sharding and the resident form ----
 def test_slabs_equal_full(gsk, ctx):
     spec = gsk.synth.config_spec("C3a", scale=0.14)
