@@ -6,9 +6,12 @@
 // of bins around the tile shell by shell; each shell's samples (contiguous 32-byte records per bin
 // row) are staged into shared memory with 1-D TMA bulk copies (cp.async.bulk → SASS UBLKCP) that
 // complete on an mbarrier, and every thread scans the staged records (broadcast LDS.128) keeping
-// its own ascending top-k list in shared memory ([slot][thread] layout, conflict-free). The CTA
-// stops when every thread's k-th distance is strictly inside the scanned block (or, for ball
-// search, the block covers the ball), so the result is the exact kNN set.
+// its own top-k list in shared memory ([slot][thread] layout, conflict-free): one 64-bit key per
+// entry (distance bits + sample index, template parameter CK) or, for ball and ranked searches,
+// exact (d², index) pairs. The CTA stops when every thread's k-th distance is strictly inside the
+// scanned block (or, for ball search, the block covers the ball), so the result is the exact kNN
+// set; tiles whose compact-key result could depend on the dropped distance bits are searched again
+// with exact keys (redo pass).
 //
 // Ordering key is (d², original sample index): d² is evaluated as ((dx·dx)+(dy·dy))+(dz·dz) with
 // round-to-nearest mul/add and no FMA — the oracle's chain — so neighbour sets are bit-identical
