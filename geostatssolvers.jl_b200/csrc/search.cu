@@ -103,9 +103,10 @@ __device__ __forceinline__ int block_excl_scan(int v, int *warp_buf, int *total)
 // nothing and never flag.
 // Launch bounds: the heap variants are asked for six CTAs per SM (<= 80 registers): left alone the compiler picks 56
 // registers and spills into the hot loop (C5 search 4.60 -> 4.49 ms per 2M targets without the spills); the insertion
-// variants stay at 72 registers (seven CTAs; at 80 the C2 search goes from 0.271 to 0.291 ms).
+// compact-key variants stay at 72 registers (seven CTAs; at 80 the C2 search goes from 0.271 to 0.291 ms); the exact-key
+// variants (ball and ranked searches, the redo pass) take up to 80 as well.
 template <int TX, int TY, int TZ, int DIM, bool HEAP, bool RANKED = false, bool CK = false>
-__global__ void __launch_bounds__(NT, HEAP ? 6 : 7) search_kernel(const GskSearchArgs a) {
+__global__ void __launch_bounds__(NT, (CK && !HEAP) ? 7 : 6) search_kernel(const GskSearchArgs a) {
   static_assert(TX * TY * TZ == NT, "tile must hold NT targets");
   static_assert(!(CK && RANKED), "ranked search keeps exact keys");
   typedef unsigned long long u64;
